@@ -1,0 +1,178 @@
+/*
+ * toda_b200.h -- C ABI of libtoda_b200.so: the B200 (sm_100a) implementation of TODA's
+ * data-parallel LiDAR hot path.
+ *
+ * Conventions (SURVEY.md section 8b, row "C-ABI"):
+ *   - extern "C", plain pointers + sizes, no torch types.
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in `_host`.
+ *   - no allocation or ownership inside the library: the caller (PyTorch on the host side)
+ *     allocates inputs, outputs and workspaces; `*_bytes()` functions size the workspaces.
+ *   - every entry point enqueues work on `stream` (a cudaStream_t passed as void*) and
+ *     returns without synchronising.
+ *   - return value: 0 = TODA_OK, negative = error; the message is in toda_last_error()
+ *     (thread-local).  There is no CPU fallback: without a CUDA device every call fails.
+ *   - entry points are re-entrant and stateless (state = caller-owned buffers).
+ *
+ * Each function cites the reference interface it replaces (file:line in rasd3/TODA).
+ */
+#ifndef TODA_B200_H
+#define TODA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TODA_OK 0
+#define TODA_ERR_INVALID (-1)
+#define TODA_ERR_CUDA (-2)
+#define TODA_ERR_WORKSPACE (-3)
+#define TODA_ERR_UNSUPPORTED (-4)
+
+#define TODA_ORDER_FIRST_APPEARANCE 0 /* voxel rows in the reference's order (order of first point) */
+#define TODA_ORDER_CANONICAL 1        /* voxel rows sorted by (b,z,y,x) */
+
+const char *toda_last_error(void);
+int toda_version(void);
+/* number of SMs / compute capability of the current device; fails when there is no CUDA device. */
+int toda_device_info(int *sm_count_host, int *cc_major_host, int *cc_minor_host);
+
+/* ------------------------------------------------------------------------------------------
+ * Occupancy index: a two-level bitmap over the (batch, D, H, W) cell grid plus per-word ranks.
+ * It is the "hash table" of this implementation: a perfect (collision-free) hash whose
+ * enumeration order IS the canonical (b,z,y,x) order, so dedup, canonical sort and
+ * coordinate -> row lookup are one structure.  Replaces the hash tables inside the un-vendored
+ * spconv package (call sites: pcdet/models/backbones_3d/spconv_backbone.py L141-146, L254-259).
+ * The buffer must be all-zero before the first insert; toda_index_release() re-zeroes exactly
+ * the words that inserts touched, so a buffer can be reused without a full memset.
+ * ------------------------------------------------------------------------------------------ */
+size_t toda_index_bytes(int batch, int D, int H, int W);
+/* mark coords[n,4] = (b,z,y,x) int32 */
+int toda_index_insert(void *index, int batch, int D, int H, int W, const int32_t *coords, int n, void *stream);
+/* mark every output cell reachable from in_coords under a conv (k,s,p): o*s = p_in + pad - k */
+int toda_index_insert_strided(void *index_out, int batch, int oD, int oH, int oW, const int32_t *in_coords, int n_in,
+                              const int *ksize_host, const int *stride_host, const int *pad_host, void *stream);
+/* ranks every marked cell; writes the sorted coordinate list (up to `cap` rows) and the number of
+ * marked cells to n_out[0] (device int32).  per-frame counts go to n_out[1..batch]. */
+int toda_index_build(void *index, int batch, int D, int H, int W, int32_t *out_coords, int cap, int32_t *n_out,
+                     void *stream);
+/* rows[i] = canonical row of coords[i], or -1 */
+int toda_index_rows(const void *index, int batch, int D, int H, int W, const int32_t *coords, int n, int32_t *rows,
+                    void *stream);
+int toda_index_release(void *index, int batch, int D, int H, int W, const int32_t *coords, int n, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1 hard voxelizer.  Replaces spconv.utils.Point2VoxelCPU3d.point_to_voxel as called from
+ * pcdet/datasets/processor/data_processor.py L36-42, L54 (VoxelGeneratorWrapper) /
+ * L115-143 (transform_points_to_voxels), for a whole batch of frames in one call.
+ *   points: row i = point_stride floats; x,y,z at columns xyz_col..xyz_col+2; the num_features
+ *           columns starting at feat_col are copied into `voxels`.  (collated `points` of
+ *           pcdet/datasets/dataset.py L173-178: stride 1+F, xyz_col = feat_col = 1.)
+ *   frame_offsets: int32[batch+1], points of frame b are rows [off[b], off[b+1]).
+ *   range_host[6] = xmin,ymin,zmin,xmax,ymax,zmax; vsize_host[3] = x,y,z; grid_host[3] = x,y,z
+ *           (= round((hi-lo)/vsize), data_processor.py L117-118).
+ * Semantics = spconv 2.x loop: c = floor((p-lo)/vsize) in fp32 with true
+ * division; a point outside [0,grid) on any axis is dropped; voxels are numbered in order of first
+ * appearance; once max_voxels exist in a frame, points of further voxels are dropped; the first
+ * max_points points (input order) of a voxel are kept.
+ * Outputs (capacity batch*max_voxels rows, frames packed back to back as np.concatenate does in
+ * dataset.py L171-178): voxels [V,max_points,F] zero padded, coords [V,4] = (b,z,y,x),
+ * num_points [V]; voxel_counts int32[batch+1] = per-frame V_b then the total V.
+ * ------------------------------------------------------------------------------------------ */
+size_t toda_voxelize_workspace_bytes(int64_t n_points, int batch, const int *grid_host, int max_points,
+                                     int max_voxels);
+int toda_voxelize_hard(const float *points, int64_t n_points, int point_stride, int xyz_col, int feat_col,
+                       int num_features, const int32_t *frame_offsets, int batch, const float *range_host,
+                       const float *vsize_host, const int *grid_host, int max_points, int max_voxels, int order,
+                       float *voxels, int32_t *coords, int32_t *num_points, int32_t *voxel_counts, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
+/* K2 MeanVFE.  pcdet/models/backbones_3d/vfe/mean_vfe.py L25-29: sum over all K slots / max(num,1).
+ * num_points is int32 when num_is_float == 0, float32 otherwise (load_data_to_gpu casts it,
+ * pcdet/models/__init__.py L34). */
+int toda_mean_vfe_fwd(const float *voxels, const void *num_points, int num_is_float, int n_voxels, int max_points,
+                      int num_features, float *voxel_features, void *stream);
+int toda_mean_vfe_bwd(const float *d_voxel_features, const void *num_points, int num_is_float, int n_voxels,
+                      int max_points, int num_features, float *d_voxels, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3 / K4 rulebooks, as neighbour tables: nbr[k*n_out + o] = input row paired with output row o
+ * under kernel offset k = (kz*KH+ky)*KW+kx, or -1.  The pair list of spconv is the set of
+ * non-negative entries.  coords must be in canonical order (toda_index_build output).
+ *   SubMConv3d  (spconv_backbone.py L12, L38-45, L78, L192): outputs == inputs.
+ *   SparseConv3d (L14-15, L90/97/104/113, L205/212/219/228): outputs from toda_index_insert_strided
+ *   + toda_index_build; nbr_fwd[kvol,n_out] gathers inputs for each output, nbr_bwd[kvol,n_in]
+ *   gives for each input the output it feeds under offset k (used by dgrad).
+ * ------------------------------------------------------------------------------------------ */
+int toda_rulebook_subm(const void *index, int batch, int D, int H, int W, const int32_t *coords, int n,
+                       const int *ksize_host, int32_t *nbr, void *stream);
+int toda_rulebook_sparse(const void *index_in, int iD, int iH, int iW, const void *index_out, int oD, int oH, int oW,
+                         int batch, const int32_t *in_coords, int n_in, const int32_t *out_coords, int n_out,
+                         const int *ksize_host, const int *stride_host, const int *pad_host, int32_t *nbr_fwd,
+                         int32_t *nbr_bwd, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5/K6/K7 sparse convolution on neighbour tables (every `conv(x)` in spconv_backbone.py).
+ *   fwd :  y[o,:]  = bias + sum_k x[nbr[k,o],:] @ w[k]        w: [kvol, Cin, Cout]
+ *   dgrad: the same entry point with dy as x, the transposed weights [kvol, Cout, Cin] and the
+ *          input-stationary table (SubM: the same table with k mirrored -- toda_weight_repack does it;
+ *          SparseConv3d: nbr_bwd).
+ *   wgrad: dw[k] = sum_o x[nbr[k,o],:]^T @ dy[o,:], written in the parameter layout
+ *          (Cout, kvol, Cin) of spconv 2.x, which pcdet/models/detectors/detector3d_template.py
+ *          L341-348 accepts.
+ * precision: TODA_CONV_FP32 = fp32 FFMA (parity path, rtol 1e-4 vs the oracle);
+ *            TODA_CONV_BF16 = bf16 operands, fp32 accumulate on tcgen05 tensor cores.
+ * ------------------------------------------------------------------------------------------ */
+#define TODA_CONV_FP32 0
+#define TODA_CONV_BF16 1
+/* param (Cout,kvol,Cin) -> [kvol,Cin,Cout] (transpose=0) or [kvol,Cout,Cin] with optional k mirroring */
+int toda_weight_repack(const float *w_param, int kvol, int cin, int cout, int transpose, int mirror_k, float *w_out,
+                       void *stream);
+int toda_spconv_fwd(const float *x, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *w,
+                    int cout, const float *bias, float *y, int precision, void *stream);
+size_t toda_spconv_wgrad_workspace_bytes(int n_out, int kvol, int cin, int cout);
+int toda_spconv_wgrad(const float *x, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *dy,
+                      int cout, float *dw_param, void *workspace, size_t workspace_bytes, int precision, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K8 BatchNorm1d(eps, momentum) + ReLU (+ residual) over (N_active, C) rows
+ * (spconv_backbone.py L23-24, L54-64, L73/L187).
+ *   stats : per-channel mean / biased var of y -> scale = gamma*rstd, shift = beta - mean*scale,
+ *           save_mean, save_rstd, running stats update (unbiased var, momentum).
+ *   apply : a = act(y*scale + shift (+ residual)).
+ *   bwd   : g = da * (a>0 if relu); dgamma = sum g*xhat; dbeta = sum g;
+ *           dy = scale*(g - dbeta/N - xhat*dgamma/N); dresidual = g.
+ * ------------------------------------------------------------------------------------------ */
+size_t toda_bn_workspace_bytes(int channels);
+int toda_bn_stats(const float *y, int n, int channels, const float *gamma, const float *beta, float eps,
+                  float momentum, float *running_mean, float *running_var, float *scale, float *shift,
+                  float *save_mean, float *save_rstd, void *workspace, size_t workspace_bytes, void *stream);
+int toda_bn_eval_coeffs(const float *gamma, const float *beta, const float *running_mean, const float *running_var,
+                        float eps, int channels, float *scale, float *shift, void *stream);
+int toda_bn_apply(const float *y, int n, int channels, const float *scale, const float *shift, const float *residual,
+                  int relu, float *a, void *stream);
+int toda_bn_bwd(const float *da, const float *a, const float *y, int n, int channels, const float *gamma,
+                const float *save_mean, const float *save_rstd, int relu, int training, float *dy, float *dresidual,
+                float *dgamma, float *dbeta, void *workspace, size_t workspace_bytes, void *stream);
+/* column sums: dbias[c] = sum_rows dy[:,c] */
+int toda_col_sum(const float *dy, int n, int channels, float *out, void *workspace, size_t workspace_bytes,
+                 void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K9 HeightCompression: pcdet/models/backbones_2d/map_to_bev/height_compression.py L20-25
+ * (SparseConvTensor.dense() + view).  out[b, c*D+z, y, x] = features[n, c]; zero elsewhere.
+ * ------------------------------------------------------------------------------------------ */
+int toda_bev_scatter_fwd(const float *features, const int32_t *coords, int n, int channels, int batch, int D, int H,
+                         int W, float *out, void *stream);
+int toda_bev_scatter_bwd(const float *d_out, const int32_t *coords, int n, int channels, int batch, int D, int H,
+                         int W, float *d_features, void *stream);
+
+/* row gather used when a SparseConvTensor arrives in non-canonical order: out[i,:] = in[rows[i],:] */
+int toda_gather_rows(const float *in, const int32_t *rows, int n, int channels, float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

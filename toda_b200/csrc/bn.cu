@@ -1,0 +1,243 @@
+// K8 BatchNorm1d (+ReLU, +residual) over (N_active, C) rows, and column sums (bias gradient).
+// All passes are HBM-bound streams over (N, C) fp32; reductions use fixed-size per-CTA partials reduced
+// in a fixed order, so results are run-to-run deterministic.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kPartials = 2 * kNumSMs;  // CTAs in the reduction grids
+
+// partial sums of up to two quantities per channel.  C <= 256; thread layout: tx = channel lane, ty = row lane.
+// mode 0: (y, y*y)      mode 1: (g, g*xhat) with g = da*(a>0)     mode 2: (dy, -)
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) col_reduce_kernel(const float *__restrict__ p0, const float *__restrict__ p1,
+                                                              const float *__restrict__ p2, int n, int c,
+                                                              const float *__restrict__ mean, const float *__restrict__ rstd,
+                                                              int relu, double *__restrict__ partial) {
+    // CTA handles rows blockIdx.x, blockIdx.x+grid, ... in chunks; threads stride over (row, channel) pairs
+    __shared__ double s0[kThreads], s1[kThreads];
+    const int cpad = c <= 16 ? 16 : (c <= 32 ? 32 : (c <= 64 ? 64 : (c <= 128 ? 128 : 256)));
+    const int rows_per_iter = kThreads / (cpad < kThreads ? cpad : kThreads);
+    const int tx = threadIdx.x % cpad, ty = threadIdx.x / cpad;
+    double a0 = 0.0, a1 = 0.0;
+    if (cpad <= kThreads) {
+        float m = 0.f, rs = 0.f;
+        if (MODE == 1 && tx < c) { m = mean[tx]; rs = rstd[tx]; }
+        for (long long r = (long long)blockIdx.x * rows_per_iter + ty; r < n; r += (long long)gridDim.x * rows_per_iter) {
+            if (tx < c) {
+                size_t e = (size_t)r * c + tx;
+                if (MODE == 0) {
+                    float v = __ldg(p0 + e);
+                    a0 += v; a1 += (double)v * v;
+                } else if (MODE == 1) {
+                    float g = __ldg(p0 + e);
+                    if (relu && !(__ldg(p1 + e) > 0.f)) g = 0.f;
+                    float xh = (__ldg(p2 + e) - m) * rs;
+                    a0 += g; a1 += (double)g * xh;
+                } else {
+                    a0 += __ldg(p0 + e);
+                }
+            }
+        }
+    }
+    s0[threadIdx.x] = a0; s1[threadIdx.x] = a1;
+    __syncthreads();
+    if (threadIdx.x < cpad && threadIdx.x < c) {
+        double t0 = 0.0, t1 = 0.0;
+        for (int j = 0; j < rows_per_iter; ++j) { t0 += s0[j * cpad + threadIdx.x]; t1 += s1[j * cpad + threadIdx.x]; }
+        partial[((size_t)blockIdx.x * 2 + 0) * c + threadIdx.x] = t0;
+        partial[((size_t)blockIdx.x * 2 + 1) * c + threadIdx.x] = t1;
+    }
+}
+
+__global__ void bn_finalize_kernel(const double *__restrict__ partial, int nblocks, int n, int c,
+                                   const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float momentum,
+                                   float *running_mean, float *running_var, float *scale, float *shift, float *save_mean,
+                                   float *save_rstd) {
+    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    double s = 0.0, ss = 0.0;
+    for (int b = 0; b < nblocks; ++b) { s += partial[((size_t)b * 2) * c + ch]; ss += partial[((size_t)b * 2 + 1) * c + ch]; }
+    double mean = n > 0 ? s / n : 0.0;
+    double var = n > 0 ? ss / n - mean * mean : 0.0;
+    if (var < 0.0) var = 0.0;
+    float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    float g = gamma ? gamma[ch] : 1.f, bt = beta ? beta[ch] : 0.f;
+    scale[ch] = g * rstd;
+    shift[ch] = bt - (float)mean * g * rstd;
+    if (save_mean) save_mean[ch] = (float)mean;
+    if (save_rstd) save_rstd[ch] = rstd;
+    if (running_mean) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)mean;
+    if (running_var) {
+        double unbiased = n > 1 ? var * n / (n - 1) : var;
+        running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
+    }
+}
+
+__global__ void bn_eval_coeffs_kernel(const float *gamma, const float *beta, const float *rm, const float *rv, float eps,
+                                      int c, float *scale, float *shift) {
+    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    float rstd = 1.0f / sqrtf(rv[ch] + eps);
+    float g = gamma ? gamma[ch] : 1.f, bt = beta ? beta[ch] : 0.f;
+    scale[ch] = g * rstd;
+    shift[ch] = bt - rm[ch] * g * rstd;
+}
+
+// a = act(y*scale + shift (+ residual)); C % 4 == 0 -> float4 path
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads) bn_apply_kernel(const float *__restrict__ y, long long total, int c,
+                                                            const float *__restrict__ scale, const float *__restrict__ shift,
+                                                            const float *__restrict__ residual, int relu, float *__restrict__ a) {
+    if (VEC) {
+        long long tv = total >> 2;
+        for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tv; e += (long long)gridDim.x * blockDim.x) {
+            int ch = (int)((e << 2) % c);
+            float4 v = __ldg((const float4 *)y + e);
+            float4 sc = __ldg((const float4 *)(scale + ch)), sh = __ldg((const float4 *)(shift + ch));
+            float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+            if (residual) {
+                float4 r = __ldg((const float4 *)residual + e);
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+            }
+            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            ((float4 *)a)[e] = o;
+        }
+    } else {
+        for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+            int ch = (int)(e % c);
+            float o = fmaf(__ldg(y + e), scale[ch], shift[ch]);
+            if (residual) o += __ldg(residual + e);
+            if (relu) o = fmaxf(o, 0.f);
+            a[e] = o;
+        }
+    }
+}
+
+__global__ void bn_bwd_finalize_kernel(const double *__restrict__ partial, int nblocks, int c, float *dgamma, float *dbeta,
+                                       float *sums /* [2c]: sum_g, sum_g_xhat */) {
+    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    double s = 0.0, sx = 0.0;
+    for (int b = 0; b < nblocks; ++b) { s += partial[((size_t)b * 2) * c + ch]; sx += partial[((size_t)b * 2 + 1) * c + ch]; }
+    if (dbeta) dbeta[ch] = (float)s;
+    if (dgamma) dgamma[ch] = (float)sx;
+    sums[ch] = (float)s;
+    sums[c + ch] = (float)sx;
+}
+
+// dy = gamma*rstd*(g - sum_g/N - xhat*sum_gx/N)   (training)   |   dy = gamma*rstd*g   (eval)
+__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float *__restrict__ da, const float *__restrict__ a,
+                                                                const float *__restrict__ y, long long total, int c, int n,
+                                                                const float *__restrict__ gamma, const float *__restrict__ mean,
+                                                                const float *__restrict__ rstd, const float *__restrict__ sums,
+                                                                int relu, int training, float *__restrict__ dy,
+                                                                float *__restrict__ dres) {
+    float inv_n = n > 0 ? 1.0f / (float)n : 0.f;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        int ch = (int)(e % c);
+        float g = __ldg(da + e);
+        if (relu && !(__ldg(a + e) > 0.f)) g = 0.f;
+        if (dres) dres[e] = g;
+        float gm = gamma ? gamma[ch] : 1.f;
+        float rs = rstd[ch];
+        float o;
+        if (training) {
+            float xh = (__ldg(y + e) - mean[ch]) * rs;
+            o = gm * rs * (g - sums[ch] * inv_n - xh * sums[c + ch] * inv_n);
+        } else {
+            o = gm * rs * g;
+        }
+        dy[e] = o;
+    }
+}
+
+__global__ void col_sum_finalize_kernel(const double *__restrict__ partial, int nblocks, int c, float *out) {
+    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += partial[((size_t)b * 2) * c + ch];
+    out[ch] = (float)s;
+}
+
+size_t bn_ws_bytes(int c) { return align_up((size_t)kPartials * 2 * c * sizeof(double) + 2 * c * sizeof(float), 256); }
+
+}  // namespace
+
+extern "C" size_t toda_bn_workspace_bytes(int channels) { return channels > 0 ? bn_ws_bytes(channels) : 0; }
+
+extern "C" int toda_bn_stats(const float *y, int n, int c, const float *gamma, const float *beta, float eps, float momentum,
+                             float *running_mean, float *running_var, float *scale, float *shift, float *save_mean,
+                             float *save_rstd, void *workspace, size_t workspace_bytes, void *stream) {
+    TODA_CHECK_ARG(n >= 0 && c > 0 && c <= 256, "bn_stats: unsupported sizes n=%d c=%d", n, c);
+    TODA_CHECK_ARG((y || n == 0) && scale && shift && workspace, "bn_stats: null pointer");
+    if (workspace_bytes < bn_ws_bytes(c)) { toda_set_error("bn_stats: workspace too small"); return TODA_ERR_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    double *partial = (double *)workspace;
+    col_reduce_kernel<0><<<kPartials, kThreads, 0, st>>>(y, nullptr, nullptr, n, c, nullptr, nullptr, 0, partial);
+    TODA_LAUNCH_OK();
+    bn_finalize_kernel<<<ceil_div(c, 128), 128, 0, st>>>(partial, kPartials, n, c, gamma, beta, eps, momentum, running_mean,
+                                                        running_var, scale, shift, save_mean, save_rstd);
+    TODA_LAUNCH_OK();
+    return TODA_OK;
+}
+
+extern "C" int toda_bn_eval_coeffs(const float *gamma, const float *beta, const float *running_mean, const float *running_var,
+                                   float eps, int c, float *scale, float *shift, void *stream) {
+    TODA_CHECK_ARG(c > 0 && running_mean && running_var && scale && shift, "bn_eval_coeffs: bad args");
+    bn_eval_coeffs_kernel<<<ceil_div(c, 128), 128, 0, (cudaStream_t)stream>>>(gamma, beta, running_mean, running_var, eps, c,
+                                                                             scale, shift);
+    TODA_LAUNCH_OK();
+    return TODA_OK;
+}
+
+extern "C" int toda_bn_apply(const float *y, int n, int c, const float *scale, const float *shift, const float *residual,
+                             int relu, float *a, void *stream) {
+    TODA_CHECK_ARG(n >= 0 && c > 0, "bn_apply: bad sizes");
+    if (n == 0) return TODA_OK;
+    TODA_CHECK_ARG(y && scale && shift && a, "bn_apply: null pointer");
+    long long total = (long long)n * c;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c % 4 == 0)
+        bn_apply_kernel<true><<<wave_grid(total / 4, kThreads), kThreads, 0, st>>>(y, total, c, scale, shift, residual, relu, a);
+    else
+        bn_apply_kernel<false><<<wave_grid(total, kThreads), kThreads, 0, st>>>(y, total, c, scale, shift, residual, relu, a);
+    TODA_LAUNCH_OK();
+    return TODA_OK;
+}
+
+extern "C" int toda_bn_bwd(const float *da, const float *a, const float *y, int n, int c, const float *gamma,
+                           const float *save_mean, const float *save_rstd, int relu, int training, float *dy, float *dresidual,
+                           float *dgamma, float *dbeta, void *workspace, size_t workspace_bytes, void *stream) {
+    TODA_CHECK_ARG(n >= 0 && c > 0 && c <= 256, "bn_bwd: unsupported sizes n=%d c=%d", n, c);
+    TODA_CHECK_ARG(save_mean && save_rstd && workspace && (n == 0 || (da && y && dy)) && (!relu || a || n == 0),
+                   "bn_bwd: null pointer");
+    if (workspace_bytes < bn_ws_bytes(c)) { toda_set_error("bn_bwd: workspace too small"); return TODA_ERR_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    double *partial = (double *)workspace;
+    float *sums = (float *)((char *)workspace + (size_t)kPartials * 2 * c * sizeof(double));
+    col_reduce_kernel<1><<<kPartials, kThreads, 0, st>>>(da, a, y, n, c, save_mean, save_rstd, relu, partial);
+    TODA_LAUNCH_OK();
+    bn_bwd_finalize_kernel<<<ceil_div(c, 128), 128, 0, st>>>(partial, kPartials, c, dgamma, dbeta, sums);
+    TODA_LAUNCH_OK();
+    if (n > 0) {
+        long long total = (long long)n * c;
+        bn_bwd_apply_kernel<<<wave_grid(total, kThreads), kThreads, 0, st>>>(da, a, y, total, c, n, gamma, save_mean, save_rstd,
+                                                                            sums, relu, training, dy, dresidual);
+        TODA_LAUNCH_OK();
+    }
+    return TODA_OK;
+}
+
+extern "C" int toda_col_sum(const float *dy, int n, int c, float *out, void *workspace, size_t workspace_bytes, void *stream) {
+    TODA_CHECK_ARG(n >= 0 && c > 0 && c <= 256 && out && workspace, "col_sum: bad args");
+    if (workspace_bytes < bn_ws_bytes(c)) { toda_set_error("col_sum: workspace too small"); return TODA_ERR_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    double *partial = (double *)workspace;
+    col_reduce_kernel<2><<<kPartials, kThreads, 0, st>>>(dy, nullptr, nullptr, n, c, nullptr, nullptr, 0, partial);
+    TODA_LAUNCH_OK();
+    col_sum_finalize_kernel<<<ceil_div(c, 128), 128, 0, st>>>(partial, kPartials, c, out);
+    TODA_LAUNCH_OK();
+    return TODA_OK;
+}

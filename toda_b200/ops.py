@@ -1,0 +1,508 @@
+"""Host-side (PyTorch) wrappers over the C ABI: tensors in, tensors out, autograd where the
+reference differentiates through the op.  PyTorch is plumbing here (device memory, streams, autograd
+graph); every device-side computation is a kernel of libtoda_b200.so.  No CPU fallback.
+"""
+import ctypes
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _C
+
+ORDER_FIRST_APPEARANCE = 0
+ORDER_CANONICAL = 1
+CONV_FP32 = 0
+CONV_BF16 = 1
+
+# launches of this library's kernels since the last reset (bench.py reports it as gpu_launches)
+_launches = 0
+
+
+def launches():
+    return _launches
+
+
+def reset_launches():
+    global _launches
+    _launches = 0
+
+
+def _count(n):
+    global _launches
+    _launches += n
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _need(t, dtype, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (toda_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+_workspaces = {}
+
+
+def _workspace(tag, nbytes, device, zero=False):
+    """Grow-only cached scratch buffers (caller-owned memory in the ABI's terms)."""
+    key = (tag, device.index)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = (torch.zeros if zero else torch.empty)(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 voxelizer
+# ------------------------------------------------------------------------------------------------
+def grid_size_xyz(pc_range, voxel_size):
+    """round((hi-lo)/vsize) -- pcdet/datasets/processor/data_processor.py L117-118."""
+    r = np.asarray(pc_range, dtype=np.float64)
+    return np.round((r[3:6] - r[0:3]) / np.asarray(voxel_size, dtype=np.float64)).astype(np.int64)
+
+
+def voxelize(points, frame_offsets, pc_range, voxel_size, max_points, max_voxels, num_features=None, xyz_col=0,
+             feat_col=0, order=ORDER_FIRST_APPEARANCE, grid=None, trim=True):
+    """Hard voxelization of a batch of frames (replaces Point2VoxelCPU3d.point_to_voxel per frame +
+    collate of dataset.py L171-178).
+
+    points: (N, stride) float32 CUDA, frames back to back; frame_offsets: int32 (B+1) CUDA tensor or list.
+    Returns voxels (V,K,F), coords (V,4)=[b,z,y,x] int32, num_points (V,) int32, counts (B+1,) int32
+    (per-frame V_b, then V).  trim=True slices to V (one host sync); trim=False returns capacity-sized
+    buffers and no sync.
+    """
+    points = _need(points, torch.float32, "points")
+    assert points.dim() == 2
+    n, stride = points.shape
+    dev = points.device
+    if not torch.is_tensor(frame_offsets):
+        frame_offsets = torch.tensor(list(frame_offsets), dtype=torch.int32, device=dev)
+    frame_offsets = _need(frame_offsets, torch.int32, "frame_offsets")
+    batch = frame_offsets.numel() - 1
+    f = int(num_features) if num_features is not None else stride - feat_col
+    grid = grid_size_xyz(pc_range, voxel_size) if grid is None else np.asarray(grid)
+    grid_c = _C.ints(grid)
+    L = _C.lib()
+    ws_bytes = L.toda_voxelize_workspace_bytes(n, batch, grid_c, max_points, max_voxels)
+    if ws_bytes == 0:
+        raise RuntimeError("toda_voxelize_workspace_bytes rejected the arguments")
+    ws = _workspace("vox", ws_bytes, dev)
+    cap = batch * max_voxels
+    voxels = torch.empty((cap, max_points, f), dtype=torch.float32, device=dev)
+    coords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    num = torch.empty((cap,), dtype=torch.int32, device=dev)
+    counts = torch.empty((batch + 1,), dtype=torch.int32, device=dev)
+    rc = L.toda_voxelize_hard(_p(points), n, stride, xyz_col, feat_col, f, _p(frame_offsets), batch,
+                              _C.floats(np.asarray(pc_range, dtype=np.float32)),
+                              _C.floats(np.asarray(voxel_size, dtype=np.float32)), grid_c, max_points, max_voxels,
+                              order, _p(voxels), _p(coords), _p(num), _p(counts), _p(ws), ws.numel(), _stream())
+    _C.check(rc, "toda_voxelize_hard")
+    _count(16 if order == ORDER_FIRST_APPEARANCE else 19)
+    if trim:
+        v = int(counts[batch].item())
+        return voxels[:v], coords[:v], num[:v], counts
+    return voxels, coords, num, counts
+
+
+class _MeanVFE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, voxels, num_points):
+        voxels = _need(voxels, torch.float32, "voxels")
+        v, k, f = voxels.shape
+        is_float = num_points.dtype == torch.float32
+        if not is_float:
+            num_points = _need(num_points, torch.int32, "voxel_num_points")
+        num_points = num_points.contiguous()
+        out = torch.empty((v, f), dtype=torch.float32, device=voxels.device)
+        _C.check(_C.lib().toda_mean_vfe_fwd(_p(voxels), _p(num_points), int(is_float), v, k, f, _p(out), _stream()),
+                 "toda_mean_vfe_fwd")
+        _count(1)
+        ctx.save_for_backward(num_points)
+        ctx.shape = (v, k, f, is_float)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (num_points,) = ctx.saved_tensors
+        v, k, f, is_float = ctx.shape
+        dout = dout.contiguous()
+        dv = torch.empty((v, k, f), dtype=torch.float32, device=dout.device)
+        _C.check(_C.lib().toda_mean_vfe_bwd(_p(dout), _p(num_points), int(is_float), v, k, f, _p(dv), _stream()),
+                 "toda_mean_vfe_bwd")
+        _count(1)
+        return dv, None
+
+
+def mean_vfe(voxels, num_points):
+    """mean_vfe.py L25-29."""
+    return _MeanVFE.apply(voxels, num_points)
+
+
+# ------------------------------------------------------------------------------------------------
+# occupancy index + rulebooks
+# ------------------------------------------------------------------------------------------------
+_index_occupant = {}   # workspace key -> the OccupancyIndex whose marks are currently in that buffer
+
+
+class OccupancyIndex:
+    """Occupancy index over (batch, D, H, W): canonical coords + coordinate->row lookup.
+
+    Index buffers are cached per (tag, dims) and shared: acquiring a buffer releases (un-marks) whatever
+    index occupied it before, and an index that lost its buffer re-marks itself on the next use, so the
+    all-zero-between-users invariant of the ABI holds without full memsets.
+    """
+
+    def __init__(self, batch, shape, device, tag):
+        self.batch = int(batch)
+        self.shape = [int(s) for s in shape]
+        d, h, w = self.shape
+        nbytes = _C.lib().toda_index_bytes(self.batch, d, h, w)
+        if nbytes == 0:
+            raise RuntimeError(f"bad index dims {batch} {shape}")
+        self.key = (("index", tag, self.batch, d, h, w), device.index)
+        self.buf = _workspace(self.key[0], nbytes, device, zero=True)
+        self.coords = None
+        self.n = 0
+        self._marked = False   # True while extra marks (not described by self.coords) may be in the buffer
+
+    def _dims(self):
+        return (self.batch, *self.shape)
+
+    def _acquire(self):
+        prev = _index_occupant.get(self.key)
+        if prev is not None and prev is not self and prev.buf.data_ptr() == self.buf.data_ptr():
+            prev._unmark()
+        _index_occupant[self.key] = self
+
+    def _unmark(self):
+        if self.coords is not None and self.n > 0:
+            _C.check(_C.lib().toda_index_release(_p(self.buf), *self._dims(), _p(self.coords), self.n, _stream()),
+                     "toda_index_release")
+            _count(1)
+        if _index_occupant.get(self.key) is self:
+            del _index_occupant[self.key]
+
+    def insert(self, coords):
+        self._acquire()
+        coords = _need(coords, torch.int32, "coords")
+        _C.check(_C.lib().toda_index_insert(_p(self.buf), *self._dims(), _p(coords), coords.shape[0], _stream()),
+                 "toda_index_insert")
+        _count(1)
+
+    def insert_strided(self, in_coords, ksize, stride, padding):
+        self._acquire()
+        in_coords = _need(in_coords, torch.int32, "in_coords")
+        _C.check(_C.lib().toda_index_insert_strided(_p(self.buf), *self._dims(), _p(in_coords), in_coords.shape[0],
+                                                    _C.ints(ksize), _C.ints(stride), _C.ints(padding), _stream()),
+                 "toda_index_insert_strided")
+        _count(1)
+
+    def build(self, cap, known_n=None):
+        """Ranks the marked cells; returns canonical coords (n,4).  Host sync to read n unless known_n."""
+        dev = self.buf.device
+        coords = torch.empty((max(cap, 1), 4), dtype=torch.int32, device=dev)
+        n_out = torch.empty((self.batch + 1,), dtype=torch.int32, device=dev)
+        _C.check(_C.lib().toda_index_build(_p(self.buf), *self._dims(), _p(coords), cap, _p(n_out), _stream()),
+                 "toda_index_build")
+        _count(5)
+        self.n = int(n_out[0].item()) if known_n is None else int(known_n)
+        self.coords = coords[:self.n]
+        self.frame_counts = n_out
+        return self.coords
+
+    def ensure_live(self):
+        """Re-marks and re-ranks this index if another index has used the shared buffer since."""
+        if _index_occupant.get(self.key) is self:
+            return
+        if self.coords is None:
+            raise RuntimeError("occupancy index was released")
+        coords, n = self.coords, self.n
+        self.insert(coords)
+        self.build(n, known_n=n)
+
+    def rows(self, coords):
+        self.ensure_live()
+        coords = _need(coords, torch.int32, "coords")
+        rows = torch.empty((coords.shape[0],), dtype=torch.int32, device=coords.device)
+        _C.check(_C.lib().toda_index_rows(_p(self.buf), *self._dims(), _p(coords), coords.shape[0], _p(rows), _stream()),
+                 "toda_index_rows")
+        _count(1)
+        return rows
+
+    def release(self):
+        if _index_occupant.get(self.key) is self:
+            self._unmark()
+        self.coords = None
+        self.n = 0
+
+
+@dataclass
+class Rulebook:
+    """Neighbour tables of one conv geometry (shared by every conv with the same indice_key)."""
+    subm: bool
+    ksize: List[int]
+    stride: List[int]
+    padding: List[int]
+    in_shape: List[int]
+    out_shape: List[int]
+    n_in: int
+    n_out: int
+    out_coords: torch.Tensor          # (n_out,4) canonical
+    nbr_fwd: torch.Tensor             # (kvol, n_out): input row per output row
+    nbr_bwd: Optional[torch.Tensor]   # (kvol, n_in): output row per input row (None for SubM: mirrored nbr_fwd)
+
+    @property
+    def kvol(self):
+        return self.ksize[0] * self.ksize[1] * self.ksize[2]
+
+
+def conv_out_size(in_size, k, s, p):
+    return (in_size + 2 * p - (k - 1) - 1) // s + 1
+
+
+def rulebook_subm(index: OccupancyIndex, ksize):
+    index.ensure_live()
+    n = index.n
+    kvol = ksize[0] * ksize[1] * ksize[2]
+    nbr = torch.empty((kvol, n), dtype=torch.int32, device=index.buf.device)
+    _C.check(_C.lib().toda_rulebook_subm(_p(index.buf), index.batch, *index.shape, _p(index.coords), n, _C.ints(ksize),
+                                         _p(nbr), _stream()), "toda_rulebook_subm")
+    _count(1)
+    return Rulebook(True, list(ksize), [1, 1, 1], [k // 2 for k in ksize], index.shape, index.shape, n, n, index.coords,
+                    nbr, None)
+
+
+def rulebook_sparse(index_in: OccupancyIndex, ksize, stride, padding, tag):
+    """Builds the output index (kept alive in the returned tuple) and both tables."""
+    index_in.ensure_live()
+    out_shape = [conv_out_size(index_in.shape[a], ksize[a], stride[a], padding[a]) for a in range(3)]
+    index_out = OccupancyIndex(index_in.batch, out_shape, index_in.buf.device, tag)
+    index_out.insert_strided(index_in.coords, ksize, stride, padding)
+    per_in = 1
+    for a in range(3):
+        per_in *= min(ksize[a], (ksize[a] + stride[a] - 1) // stride[a])
+    cells = index_in.batch * out_shape[0] * out_shape[1] * out_shape[2]
+    cap = int(min(index_in.n * per_in, cells))
+    out_coords = index_out.build(cap)
+    n_in, n_out = index_in.n, index_out.n
+    kvol = ksize[0] * ksize[1] * ksize[2]
+    dev = index_in.buf.device
+    nbr_fwd = torch.empty((kvol, n_out), dtype=torch.int32, device=dev)
+    nbr_bwd = torch.empty((kvol, n_in), dtype=torch.int32, device=dev)
+    _C.check(_C.lib().toda_rulebook_sparse(_p(index_in.buf), *index_in.shape, _p(index_out.buf), *out_shape, index_in.batch,
+                                           _p(index_in.coords), n_in, _p(out_coords), n_out, _C.ints(ksize),
+                                           _C.ints(stride), _C.ints(padding), _p(nbr_fwd), _p(nbr_bwd), _stream()),
+             "toda_rulebook_sparse")
+    _count(2)
+    rb = Rulebook(False, list(ksize), list(stride), list(padding), index_in.shape, out_shape, n_in, n_out, out_coords,
+                  nbr_fwd, nbr_bwd)
+    return rb, index_out
+
+
+# ------------------------------------------------------------------------------------------------
+# K5-K7 sparse convolution
+# ------------------------------------------------------------------------------------------------
+def _repack(weight, transpose, mirror):
+    cout, kvol, cin = weight.shape[0], weight.shape[1] * weight.shape[2] * weight.shape[3], weight.shape[4]
+    out = torch.empty((kvol, cout, cin) if transpose else (kvol, cin, cout), dtype=torch.float32, device=weight.device)
+    _C.check(_C.lib().toda_weight_repack(_p(weight), kvol, cin, cout, int(transpose), int(mirror), _p(out), _stream()),
+             "toda_weight_repack")
+    _count(1)
+    return out
+
+
+def _conv_call(x, cin, nbr, n_out, kvol, w, cout, bias, precision):
+    y = torch.empty((n_out, cout), dtype=torch.float32, device=x.device)
+    _C.check(_C.lib().toda_spconv_fwd(_p(x), x.shape[0], cin, _p(nbr), n_out, kvol, _p(w), cout, _p(bias), _p(y),
+                                      precision, _stream()), "toda_spconv_fwd")
+    _count(1)
+    return y
+
+
+class _SparseConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, rb: Rulebook, precision):
+        x = _need(x.contiguous(), torch.float32, "features")
+        weight = _need(weight.contiguous(), torch.float32, "weight")
+        cout, cin = weight.shape[0], weight.shape[4]
+        assert x.shape == (rb.n_in, cin), (x.shape, rb.n_in, cin)
+        w = _repack(weight, False, False)
+        b = bias.contiguous() if bias is not None else None
+        y = _conv_call(x, cin, rb.nbr_fwd, rb.n_out, rb.kvol, w, cout, b, precision)
+        ctx.save_for_backward(x, weight)
+        ctx.rb, ctx.precision, ctx.has_bias = rb, precision, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        rb, precision = ctx.rb, ctx.precision
+        cout, cin = weight.shape[0], weight.shape[4]
+        dy = dy.contiguous()
+        L = _C.lib()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            # dgrad = the same gather-GEMM on the input-stationary table with transposed weights
+            wt = _repack(weight, True, rb.subm)
+            table = rb.nbr_fwd if rb.subm else rb.nbr_bwd
+            dx = _conv_call(dy, cout, table, rb.n_in, rb.kvol, wt, cin, None, precision)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(weight)
+            ws_bytes = L.toda_spconv_wgrad_workspace_bytes(rb.n_out, rb.kvol, cin, cout)
+            ws = _workspace("wgrad", ws_bytes, dy.device)
+            _C.check(L.toda_spconv_wgrad(_p(x), rb.n_in, cin, _p(rb.nbr_fwd), rb.n_out, rb.kvol, _p(dy), cout, _p(dw), _p(ws),
+                                         ws.numel(), precision, _stream()), "toda_spconv_wgrad")
+            _count(2)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = col_sum(dy)
+        return dx, dw, db, None, None
+
+
+def sparse_conv(x, weight, bias, rb, precision=CONV_FP32):
+    return _SparseConv.apply(x, weight, bias, rb, precision)
+
+
+def col_sum(t):
+    n, c = t.shape
+    out = torch.empty((c,), dtype=torch.float32, device=t.device)
+    L = _C.lib()
+    ws = _workspace("bn", L.toda_bn_workspace_bytes(c), t.device)
+    _C.check(L.toda_col_sum(_p(t), n, c, _p(out), _p(ws), ws.numel(), _stream()), "toda_col_sum")
+    _count(2)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# K8 BatchNorm + ReLU (+ residual)
+# ------------------------------------------------------------------------------------------------
+class _BNAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, gamma, beta, running_mean, running_var, eps, momentum, training, residual, relu):
+        y = _need(y.contiguous(), torch.float32, "bn input")
+        n, c = y.shape
+        dev = y.device
+        L = _C.lib()
+        scale = torch.empty((c,), dtype=torch.float32, device=dev)
+        shift = torch.empty_like(scale)
+        ws = _workspace("bn", L.toda_bn_workspace_bytes(c), dev)
+        if training:
+            mean = torch.empty_like(scale)
+            rstd = torch.empty_like(scale)
+            _C.check(L.toda_bn_stats(_p(y), n, c, _p(gamma), _p(beta), float(eps), float(momentum), _p(running_mean),
+                                     _p(running_var), _p(scale), _p(shift), _p(mean), _p(rstd), _p(ws), ws.numel(),
+                                     _stream()), "toda_bn_stats")
+            _count(2)
+        else:
+            _C.check(L.toda_bn_eval_coeffs(_p(gamma), _p(beta), _p(running_mean), _p(running_var), float(eps), c, _p(scale),
+                                           _p(shift), _stream()), "toda_bn_eval_coeffs")
+            _count(1)
+            mean = running_mean
+            rstd = torch.rsqrt(running_var + eps) if y.requires_grad or gamma.requires_grad else None
+        res = residual.contiguous() if residual is not None else None
+        a = torch.empty_like(y)
+        _C.check(L.toda_bn_apply(_p(y), n, c, _p(scale), _p(shift), _p(res), int(relu), _p(a), _stream()), "toda_bn_apply")
+        _count(1)
+        ctx.save_for_backward(y, a, gamma, mean, rstd)
+        ctx.cfg = (bool(training), bool(relu), residual is not None)
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        y, a, gamma, mean, rstd = ctx.saved_tensors
+        training, relu, has_res = ctx.cfg
+        n, c = y.shape
+        da = da.contiguous()
+        L = _C.lib()
+        dy = torch.empty_like(y)
+        dres = torch.empty_like(y) if has_res else None
+        dgamma = torch.empty((c,), dtype=torch.float32, device=y.device)
+        dbeta = torch.empty_like(dgamma)
+        ws = _workspace("bn", L.toda_bn_workspace_bytes(c), y.device)
+        _C.check(L.toda_bn_bwd(_p(da), _p(a), _p(y), n, c, _p(gamma), _p(mean), _p(rstd), int(relu), int(training), _p(dy),
+                               _p(dres), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _stream()), "toda_bn_bwd")
+        _count(3)
+        return dy, dgamma, dbeta, None, None, None, None, None, dres, None
+
+
+def bn_act(y, bn: torch.nn.BatchNorm1d, residual=None, relu=True):
+    """BatchNorm1d (+ residual) (+ ReLU) with the module's parameters / running stats
+    (spconv_backbone.py L23-24, L54-64)."""
+    training = bn.training or bn.running_mean is None
+    if training and bn.running_mean is not None and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return _BNAct.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, training, residual,
+                        relu)
+
+
+# ------------------------------------------------------------------------------------------------
+# K9 BEV scatter
+# ------------------------------------------------------------------------------------------------
+class _BEVScatter(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, features, coords, batch, d, h, w):
+        features = _need(features.contiguous(), torch.float32, "features")
+        coords = _need(coords, torch.int32, "indices")
+        n, c = features.shape
+        out = torch.empty((batch, c * d, h, w), dtype=torch.float32, device=features.device)
+        _C.check(_C.lib().toda_bev_scatter_fwd(_p(features), _p(coords), n, c, batch, d, h, w, _p(out), _stream()),
+                 "toda_bev_scatter_fwd")
+        _count(2)
+        ctx.save_for_backward(coords)
+        ctx.dims = (n, c, batch, d, h, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (coords,) = ctx.saved_tensors
+        n, c, batch, d, h, w = ctx.dims
+        dout = dout.contiguous()
+        df = torch.empty((n, c), dtype=torch.float32, device=dout.device)
+        _C.check(_C.lib().toda_bev_scatter_bwd(_p(dout), _p(coords), n, c, batch, d, h, w, _p(df), _stream()),
+                 "toda_bev_scatter_bwd")
+        _count(1)
+        return df, None, None, None, None, None
+
+
+def bev_scatter(features, coords, batch, d, h, w):
+    """(B, C*D, H, W) dense BEV map; height_compression.py L20-25."""
+    return _BEVScatter.apply(features, coords, batch, d, h, w)
+
+
+class _GatherRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, rows, inverse_rows):
+        x = _need(x.contiguous(), torch.float32, "features")
+        n, c = rows.shape[0], x.shape[1]
+        out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        _C.check(_C.lib().toda_gather_rows(_p(x), _p(rows), n, c, _p(out), _stream()), "toda_gather_rows")
+        _count(1)
+        ctx.save_for_backward(inverse_rows)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (inv,) = ctx.saved_tensors
+        dout = dout.contiguous()
+        n, c = inv.shape[0], dout.shape[1]
+        dx = torch.empty((n, c), dtype=torch.float32, device=dout.device)
+        _C.check(_C.lib().toda_gather_rows(_p(dout), _p(inv), n, c, _p(dx), _stream()), "toda_gather_rows")
+        _count(1)
+        return dx, None, None
+
+
+def permute_rows(x, rows, inverse_rows):
+    """out[i] = x[rows[i]] for a permutation `rows` (inverse given, used by the backward)."""
+    return _GatherRows.apply(x, rows, inverse_rows)

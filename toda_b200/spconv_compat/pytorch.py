@@ -1,0 +1,234 @@
+"""`spconv.pytorch`-shaped surface on top of libtoda_b200 (the drop-in contract of SURVEY.md section 8b).
+
+Exactly the names the reference touches: SparseConvTensor (features / indices / spatial_shape /
+batch_size / dense() / replace_feature()), SubMConv3d, SparseConv3d, SparseInverseConv3d, SparseSequential,
+SparseModule and conv.SparseConvolution (pcdet/utils/spconv_utils.py L3-6, L19, L29-31;
+pcdet/models/backbones_3d/spconv_backbone.py L12-21, L30, L38-45, L141-146; height_compression.py L21).
+
+Row order: a SparseConvTensor keeps the caller's row order until its first convolution; convolution
+outputs are in canonical (b,z,y,x) order with their own consistent `indices` (spconv leaves the order of
+SparseConv3d outputs implementation-defined; for SubMConv3d it preserves the input order, which coincides
+whenever the input is canonical, e.g. when it comes from toda_b200's voxelizer in canonical order).
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+_precision = ops.CONV_FP32
+
+
+def set_conv_precision(p):
+    """'fp32' (FFMA, parity path) or 'bf16' (tcgen05 tensor cores, fp32 accumulate)."""
+    global _precision
+    _precision = {"fp32": ops.CONV_FP32, "bf16": ops.CONV_BF16}[p] if isinstance(p, str) else int(p)
+
+
+def get_conv_precision():
+    return _precision
+
+
+def _triple(v):
+    if isinstance(v, (list, tuple)):
+        assert len(v) == 3
+        return [int(x) for x in v]
+    return [int(v)] * 3
+
+
+class SparseConvTensor:
+    def __init__(self, features, indices, spatial_shape, batch_size, grid=None, voxel_num=None, indice_dict=None,
+                 benchmark=False, _index=None):
+        self.features = features
+        self.indices = indices
+        self.spatial_shape = [int(s) for s in spatial_shape]
+        self.batch_size = int(batch_size)
+        self.indice_dict = indice_dict if indice_dict is not None else {}
+        self.grid = grid
+        self.voxel_num = voxel_num
+        self.benchmark = benchmark
+        self._index = _index          # ops.OccupancyIndex when rows are in canonical order
+
+    def replace_feature(self, feature):
+        return SparseConvTensor(feature, self.indices, self.spatial_shape, self.batch_size, self.grid, self.voxel_num,
+                                self.indice_dict, self.benchmark, self._index)
+
+    @property
+    def spatial_size(self):
+        return int(np.prod(self.spatial_shape))
+
+    def canonical(self, assume_canonical=False):
+        """This tensor with rows in (b,z,y,x) order and a live occupancy index."""
+        if self._index is not None:
+            return self
+        indices = self.indices
+        if indices.dtype != torch.int32:
+            indices = indices.int()
+        indices = indices.contiguous()
+        n = indices.shape[0]
+        index = ops.OccupancyIndex(self.batch_size, self.spatial_shape, indices.device, "level")
+        index.insert(indices)
+        coords = index.build(n)
+        if index.n != n:
+            raise ValueError(f"SparseConvTensor indices hold {n - index.n} duplicate or out-of-range coordinates")
+        if assume_canonical or bool(torch.equal(coords, indices)):
+            feats = self.features
+        else:
+            rows = index.rows(indices)                       # canonical row of every input row
+            inv = torch.empty_like(rows)
+            inv[rows.long()] = torch.arange(n, dtype=torch.int32, device=rows.device)
+            feats = ops.permute_rows(self.features, inv, rows)
+        return SparseConvTensor(feats, coords, self.spatial_shape, self.batch_size, self.grid, self.voxel_num,
+                                self.indice_dict, self.benchmark, index)
+
+    def dense(self, channels_first=True):
+        """zeros (B,C,D,H,W) with features scattered in (Appendix C.3)."""
+        idx = self.indices if self.indices.dtype == torch.int32 else self.indices.int()
+        d, h, w = self.spatial_shape
+        c = self.features.shape[1]
+        out = ops.bev_scatter(self.features, idx.contiguous(), self.batch_size, d, h, w).view(self.batch_size, c, d, h, w)
+        if not channels_first:
+            return out.permute(0, 2, 3, 4, 1).contiguous()
+        return out
+
+
+class SparseModule(nn.Module):
+    """Marker base: SparseSequential hands the whole SparseConvTensor to these."""
+    pass
+
+
+class SparseSequential(SparseModule):
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        if len(args) == 1 and isinstance(args[0], OrderedDict):
+            for key, module in args[0].items():
+                self.add_module(key, module)
+        else:
+            for i, module in enumerate(args):
+                self.add_module(str(i), module)
+        for name, module in kwargs.items():
+            self.add_module(name, module)
+
+    def __getitem__(self, idx):
+        return list(self._modules.values())[idx]
+
+    def __len__(self):
+        return len(self._modules)
+
+    def add(self, module, name=None):
+        self.add_module(name if name is not None else str(len(self._modules)), module)
+
+    def forward(self, x):
+        mods = list(self._modules.values())
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, SparseModule):
+                x = m(x)
+                i += 1
+            elif isinstance(x, SparseConvTensor):
+                if x.indices.shape[0] == 0:
+                    i += 1
+                    continue
+                # BatchNorm1d [+ ReLU] after a conv: one fused pass of libtoda_b200 instead of ATen's
+                if type(m) is nn.BatchNorm1d and m.affine and m.track_running_stats and x.features.is_cuda:
+                    relu = i + 1 < len(mods) and type(mods[i + 1]) is nn.ReLU
+                    x = x.replace_feature(ops.bn_act(x.features, m, None, relu))
+                    i += 2 if relu else 1
+                else:
+                    x = x.replace_feature(m(x.features))
+                    i += 1
+            else:
+                x = m(x)
+                i += 1
+        return x
+
+
+class SparseConvolution(SparseModule):
+    """weight: (Cout, kz, ky, kx, Cin) (accepted by detector3d_template.py L341-348); bias: (Cout,)."""
+
+    def __init__(self, ndim, in_channels, out_channels, kernel_size=3, stride=1, padding=0, dilation=1, groups=1,
+                 bias=True, subm=False, output_padding=0, transposed=False, inverse=False, indice_key=None, algo=None,
+                 fp32_accum=None, name=None):
+        super().__init__()
+        if ndim != 3 or groups != 1 or transposed or inverse or _triple(dilation) != [1, 1, 1]:
+            raise NotImplementedError("toda_b200 supports 3-D, dense-group, dilation-1 sparse convolutions")
+        self.ndim = ndim
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = _triple(kernel_size)
+        self.stride = _triple(stride)
+        self.padding = _triple(padding)
+        self.dilation = [1, 1, 1]
+        self.subm = subm
+        self.indice_key = indice_key
+        self.weight = nn.Parameter(torch.empty(out_channels, *self.kernel_size, in_channels))
+        if bias:
+            self.bias = nn.Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            fan_in = self.in_channels * int(np.prod(self.kernel_size))
+            bound = 1 / math.sqrt(fan_in)
+            nn.init.uniform_(self.bias, -bound, bound)
+
+    def extra_repr(self):
+        return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}, "
+                f"padding={self.padding}, subm={self.subm}, indice_key={self.indice_key}")
+
+    def _rulebook(self, x):
+        key = self.indice_key
+        hit = x.indice_dict.get(key) if key is not None else None
+        if hit is not None:
+            rb, index_out = hit
+            geom_ok = (rb.subm == self.subm and rb.ksize == self.kernel_size and rb.in_shape == x.spatial_shape
+                       and rb.n_in == x.features.shape[0] and (self.subm or (rb.stride == self.stride and rb.padding == self.padding)))
+            if geom_ok:
+                return rb, index_out
+        if self.subm:
+            rb = ops.rulebook_subm(x._index, self.kernel_size)
+            index_out = x._index
+        else:
+            rb, index_out = ops.rulebook_sparse(x._index, self.kernel_size, self.stride, self.padding, ("out", str(key)))
+        if key is not None:
+            x.indice_dict[key] = (rb, index_out)
+        return rb, index_out
+
+    def forward(self, x):
+        assert isinstance(x, SparseConvTensor)
+        x = x.canonical()
+        rb, index_out = self._rulebook(x)
+        y = ops.sparse_conv(x.features, self.weight, self.bias, rb, _precision)
+        return SparseConvTensor(y, rb.out_coords, rb.out_shape, x.batch_size, x.grid, x.voxel_num, x.indice_dict,
+                                x.benchmark, index_out)
+
+
+class SubMConv3d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None, algo=None, fp32_accum=None, name=None):
+        super().__init__(3, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias, True,
+                         indice_key=indice_key)
+        if self.stride != [1, 1, 1]:
+            raise NotImplementedError("SubMConv3d requires stride 1")
+
+
+class SparseConv3d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None, algo=None, fp32_accum=None, name=None):
+        super().__init__(3, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias, False,
+                         indice_key=indice_key)
+
+
+class SparseInverseConv3d(SparseModule):
+    """Named by post_act_block's unused 'inverseconv' branch only (spconv_backbone.py L16-17); not on the hot path."""
+
+    def __init__(self, *a, **kw):
+        super().__init__()
+        raise NotImplementedError("SparseInverseConv3d is outside the hot path (SURVEY.md section 8b)")
