@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the hot path on B200 (BASELINE.json metric), one JSON line on stdout.
+
+Workload (config.workload): BASELINE.json configs[2] -- "CenterPoint VoxelResBackBone8x fwd+bwd, nuScenes
+0.075 m grid 1440x1440x41, batch 4/GPU": one step = hard-voxelize 4 synthetic nuScenes-shaped 10-sweep frames
+(K1) -> MeanVFE (K2) -> rulebooks (K3/K4) -> VoxelResBackBone8x forward, train-mode BatchNorm (K5/K8) ->
+HeightCompression (K9) -> backward to voxel_features and every parameter (K6/K7/K8) -> gradient all-reduce
+(N>1 only).  `value` = frames/s with the points resident in HBM; `e2e` = the same step fed from pinned HOST
+memory through the plugin modules, H2D copy and a D2H read of the loss inside the timed region.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision fp32|bf16]
+Under torchrun every rank runs its own 4 frames (weak scaling); rank 0 prints the line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from toda_b200 import synth  # noqa: E402
+
+WORKLOAD = "nus_0075"
+FRAMES_PER_GPU = 4
+POOL = 3                     # distinct pre-staged batches rotated through, so no step re-reads a warm input
+METRIC = "frames/s voxelize+VoxelResBackBone8x fwd+bwd"
+
+
+class Cfg(dict):
+    __getattr__ = dict.get
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"], bf16_tflops_sustained=p.get("bf16_tflops_sustained"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------------
+def build_hot_path(device, precision):
+    import toda_b200.pcdet_plugin as P
+    from toda_b200.spconv_compat import pytorch as sp
+    sp.set_conv_precision(precision)
+    cfg = synth.CONFIGS[WORKLOAD]
+    grid = synth.grid_size_xyz(cfg["pc_range"], cfg["voxel_size"])
+    torch.manual_seed(666)   # the reference's --fix_random_seed value
+    vfe = P.MeanVFE(Cfg(MAX_POINTS_PER_VOXEL=cfg["max_points"], MAX_NUMBER_OF_VOXELS=cfg["max_voxels"]), cfg["num_features"],
+                    voxel_size=cfg["voxel_size"], point_cloud_range=cfg["pc_range"], grid_size=grid)
+    net = P.VoxelResBackBone8x(Cfg(), cfg["num_features"], grid)
+    hc = P.HeightCompression(Cfg(NUM_BEV_FEATURES=256))
+    for m in (vfe, net, hc):
+        m.to(device).train()
+    return vfe, net, hc
+
+
+def host_batches(rank, n_batches):
+    """Pinned host copies of collated `points` [b,x,y,z,i,dt] (dataset.py L173-178) + frame offsets."""
+    out = []
+    for j in range(n_batches):
+        first = (rank * POOL + j) * FRAMES_PER_GPU
+        frames, collated = synth.make_batch(WORKLOAD, FRAMES_PER_GPU, first_frame=first)
+        offs = np.cumsum([0] + [f.shape[0] for f in frames]).astype(np.int32)
+        out.append((torch.from_numpy(collated).pin_memory(), torch.from_numpy(offs).pin_memory()))
+    return out
+
+
+def run_ours(args, rank, world, local_rank):
+    from toda_b200 import ops
+    from toda_b200.dist import FlatGradBucket
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    vfe, net, hc = build_hot_path(device, args.precision)
+    bucket = FlatGradBucket(net.parameters())
+    hosts = host_batches(rank, POOL)
+    devs = [(p.to(device), o.to(device)) for p, o in hosts]
+    cot = None
+
+    def step(points, offsets):
+        nonlocal cot
+        bucket.zero()
+        bd = {"points": points, "point_frame_offsets": offsets, "batch_size": FRAMES_PER_GPU}
+        bd = hc(net(vfe(bd)))
+        sf = bd["spatial_features"]
+        if cot is None:
+            cot = torch.randn(sf.shape, device=device, generator=torch.Generator(device=device).manual_seed(1)) / sf.numel()
+        loss = (sf * cot).sum()
+        loss.backward()
+        bucket.all_reduce_mean()
+        return loss, bd
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm -----------------------------------------------------------------------------
+    for i in range(args.warmup):
+        step(*devs[i % POOL])
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ops.reset_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss, bd = step(*devs[i % POOL])
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = e0.elapsed_time(e1)
+    launches = ops.launches()
+    t = torch.tensor([ms], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * FRAMES_PER_GPU * args.steps / (ms / 1e3)
+
+    # ---- end-to-end arm: pinned host points -> H2D -> step -> D2H loss -----------------------------------
+    def e2e_step(i):
+        hp, ho = hosts[i % POOL]
+        loss, _ = step(hp.to(device, non_blocking=True), ho.to(device, non_blocking=True))
+        return float(loss.item())
+    for i in range(max(1, args.warmup // 2)):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    h2d = int(np.mean([p.numel() * 4 + o.numel() * 4 for p, o in hosts]))
+    e2e = dict(value=world * FRAMES_PER_GPU * args.steps / (e2e_ms / 1e3), unit="frames/s", h2d_bytes_per_step=h2d,
+               d2h_bytes_per_step=4 + 4 * 8, ms_per_step=e2e_ms / args.steps)
+
+    if rank != 0:
+        return None
+    # ---- roofline pass (rank 0): per-call device times of one more step, not part of `value` ----------------
+    peaks = load_peaks()
+    ops.profile_begin()
+    loss, bd = step(*devs[0])
+    prof = ops.profile_end()
+    roof, layers = roofline_from_profile(prof, bd, peaks, ms / args.steps)
+    line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32" if args.precision == "fp32" else "bf16", data="synthetic",
+                config=dict(workload="BASELINE.json configs[2]: CenterPoint VoxelResBackBone8x fwd+bwd, nuScenes-shaped 10-sweep "
+                                     "frames, 0.075 m voxels, grid 1440x1440x41, batch 4/GPU, train-mode BN, K=10, max_voxels 120000",
+                            frames_per_gpu=FRAMES_PER_GPU, points_per_frame=int(hosts[0][0].shape[0] / FRAMES_PER_GPU),
+                            voxels_per_frame=int(bd["voxel_coords"].shape[0] / FRAMES_PER_GPU), conv_precision=args.precision,
+                            l2="inputs rotate over %d pre-staged batches and each step streams >1 GB of activations (>> 126 MB L2)" % POOL,
+                            parallelism=f"dp{world} (frame-sharded, flat-bucket grad all-reduce)"),
+                clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roof, roofline_layers=layers)
+    return line
+
+
+def roofline_from_profile(prof, bd, peaks, step_ms):
+    """Algorithmic flops / bytes per call (SURVEY.md section 8d formulas) over the measured call durations."""
+    from collections import defaultdict
+    pairs_cache = {}
+
+    def pairs_of(rb_id):
+        return pairs_cache.get(rb_id)
+    # pair counts per rulebook (computed outside any timed region)
+    for key, (rb, _) in bd["encoded_spconv_tensor"].indice_dict.items():
+        pairs_cache[id(rb)] = int((rb.nbr_fwd >= 0).sum().item())
+    groups = defaultdict(lambda: dict(ms=0.0, calls=0, flops=0.0, bytes=0.0))
+    for r in prof:
+        name = r["name"]
+        g = None
+        if name in ("conv_fwd", "conv_dgrad", "conv_wgrad"):
+            P = pairs_of(r["rb"]) or 0
+            e = 4 if r["precision"] == 0 else 2
+            flops = 2.0 * P * r["cin"] * r["cout"]
+            byts = e * (r["n_in"] * r["cin"] + r["n_out"] * r["cout"]) + 8.0 * P + e * r["kvol"] * r["cin"] * r["cout"]
+            key = f"{name} {r['cin']}->{r['cout']} k{r['kvol']}"
+            g = groups[key]
+            g["flops"] += flops
+            g["bytes"] += byts
+            g["kind"] = "conv"
+        elif name == "voxelize":
+            v = bd["voxel_coords"].shape[0]
+            byts = 4.0 * r["n_points"] * r["F"] + 4.0 * v * r["K"] * r["F"] + 16.0 * v + 4.0 * v
+            g = groups[name]
+            g["bytes"] += byts
+            g["kind"] = "hbm"
+        elif name in ("bn_apply", "bn_stats", "bn_bwd", "mean_vfe_fwd", "bev_scatter_fwd", "bev_scatter_bwd", "rulebook_subm",
+                      "rulebook_sparse", "index_build"):
+            g = groups[name]
+            g["kind"] = "hbm"
+            if name == "bn_apply":
+                g["bytes"] += 4.0 * r["n"] * r["c"] * (3 if r["residual"] else 2)
+            elif name == "bn_stats":
+                g["bytes"] += 4.0 * r["n"] * r["c"]
+            elif name == "bn_bwd":
+                g["bytes"] += 4.0 * r["n"] * r["c"] * (8 if r["residual"] else 7)
+            elif name == "mean_vfe_fwd":
+                g["bytes"] += 4.0 * r["V"] * r["K"] * r["F"] + 4.0 * r["V"] + 4.0 * r["V"] * r["F"]
+            elif name == "bev_scatter_fwd":
+                g["bytes"] += 4.0 * r["n"] * r["c"] + 16.0 * r["n"] + 4.0 * r["out_elems"]
+            elif name == "bev_scatter_bwd":
+                g["bytes"] += 8.0 * r["n"] * r["c"] + 16.0 * r["n"]
+            elif name == "rulebook_subm":
+                g["bytes"] += 16.0 * r["n"] + 4.0 * r["kvol"] * r["n"]
+            elif name == "rulebook_sparse":
+                g["bytes"] += 16.0 * (r["n_in"] + r["n_out"]) + 4.0 * r["kvol"] * (r["n_in"] + r["n_out"])
+        if g is not None:
+            g["ms"] += r["ms"]
+            g["calls"] += 1
+    total_ms = sum(g["ms"] for g in groups.values())
+    layers = []
+    for key, g in sorted(groups.items(), key=lambda kv: -kv[1]["ms"]):
+        row = dict(kernel=key, calls=g["calls"], ms=round(g["ms"], 4), share_of_profiled=round(g["ms"] / max(total_ms, 1e-9), 4))
+        if g["ms"] > 0:
+            if g.get("kind") == "conv":
+                row["tflops"] = round(g["flops"] / (g["ms"] * 1e-3) / 1e12, 3)
+                row["frac_of_bf16_peak"] = round(row["tflops"] / peaks["bf16_tflops_sustained"], 5)
+                row["gbs"] = round(g["bytes"] / (g["ms"] * 1e-3) / 1e9, 1)
+            elif g["bytes"] > 0:
+                row["gbs"] = round(g["bytes"] / (g["ms"] * 1e-3) / 1e9, 1)
+                row["frac_of_hbm_peak"] = round(row["gbs"] / peaks["hbm_gbs"], 4)
+        layers.append(row)
+    top_key, top = max(groups.items(), key=lambda kv: kv[1]["ms"])
+    if top.get("kind") == "conv":
+        achieved = top["flops"] / top["calls"] / (top["ms"] / top["calls"] * 1e-3) / 1e12
+        roof = dict(bound="tensor", kernel=top_key, achieved=achieved, peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s",
+                    frac=achieved / peaks["bf16_tflops_sustained"], traffic=None, peak_source=peaks["source"] + ", sustained bf16",
+                    launches=top["calls"], avg_launch_ms=top["ms"] / top["calls"], share_of_step=top["ms"] / step_ms)
+    else:
+        achieved = top["bytes"] / top["calls"] / (top["ms"] / top["calls"] * 1e-3) / 1e9
+        roof = dict(bound="hbm", kernel=top_key, achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"],
+                    traffic=None, peak_source=peaks["source"], launches=top["calls"], avg_launch_ms=top["ms"] / top["calls"],
+                    share_of_step=top["ms"] / step_ms)
+    return roof, layers
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's path, on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_step_time(n_frames, steps, warmup):
+    """Seconds per step of the CPU path on `n_frames` full-size frames: voxelize (C restatement of the
+    Point2VoxelCPU3d loop, one thread per frame as a DataLoader worker would) + MeanVFE + VoxelResBackBone8x
+    fwd+bwd + HeightCompression through the oracle's pure-PyTorch sparse conv (all host threads)."""
+    from oracle import voxelize as OV
+    from tests import parity_utils as PU
+    cfg = synth.CONFIGS[WORKLOAD]
+    grid = synth.grid_size_xyz(cfg["pc_range"], cfg["voxel_size"])
+    torch.manual_seed(666)
+    net = PU.oracle_backbones()["VoxelResBackBone8x"](Cfg(), cfg["num_features"], grid)
+    net.train()
+    gens = [OV.Point2VoxelCPU3d(cfg["voxel_size"], cfg["pc_range"], cfg["num_features"], cfg["max_points"], cfg["max_voxels"]["train"])
+            for _ in range(n_frames)]
+    frames = [synth.make_frame(WORKLOAD, i) for i in range(n_frames)]
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        outs = [[t.numpy() for t in g.point_to_voxel(OV.from_numpy(f))] for g, f in zip(gens, frames)]
+        voxels = np.concatenate([o[0] for o in outs])
+        num = np.concatenate([o[2] for o in outs])
+        coords = np.concatenate([np.pad(o[1], ((0, 0), (1, 0)), constant_values=b) for b, o in enumerate(outs)])
+        vf = torch.from_numpy(OV.mean_vfe(voxels, num)).requires_grad_(True)
+        for p in net.parameters():
+            p.grad = None
+        bd = PU._oracle_hc(net({"voxel_features": vf, "voxel_coords": torch.from_numpy(coords).float(), "batch_size": n_frames}))
+        sf = bd["spatial_features"]
+        (sf * (1.0 / sf.numel())).sum().backward()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return float(np.mean(times)), int(voxels.shape[0])
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return None
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sec, nvox = cpu_step_time(1, args.steps, args.warmup)
+    value = 1.0 / sec
+    cpu = dict(value=value, unit="frames/s", cores=cores, kind="port",
+               sample="1 full-size nuScenes-shaped frame per step (of the 4-frame batch): C voxelizer loop + MeanVFE + "
+                      "oracle VoxelResBackBone8x fwd+bwd + dense BEV, torch CPU threads=%d; spconv itself is not installable" % cores)
+    return dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                impl="reference", config=dict(workload="BASELINE.json configs[2] (same as the GPU arm), one frame per CPU step",
+                                              voxels_per_frame=nvox),
+                cpu_baseline=cpu, e2e=dict(value=value, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("TODA_CONV_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        line = run_reference(args, rank, world)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: toda_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    line = run_ours(args, rank, world, local_rank)
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            sec, nvox = cpu_step_time(1, 1, 0)
+            line["cpu_baseline"] = dict(value=1.0 / sec, unit="frames/s", cores=cores, kind="port",
+                                        sample="one full-size frame, one step (%.1f s): C voxelizer loop + MeanVFE + oracle "
+                                               "VoxelResBackBone8x fwd+bwd + dense BEV on torch CPU" % sec)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

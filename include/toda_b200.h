@@ -130,9 +130,11 @@ int toda_rulebook_sparse(const void *index_in, int iD, int iH, int iW, const voi
 /* param (Cout,kvol,Cin) -> [kvol,Cin,Cout] (transpose=0) or [kvol,Cout,Cin] with optional k mirroring */
 int toda_weight_repack(const float *w_param, int kvol, int cin, int cout, int transpose, int mirror_k, float *w_out,
                        void *stream);
+size_t toda_spconv_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol, int precision);
 int toda_spconv_fwd(const float *x, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *w,
-                    int cout, const float *bias, float *y, int precision, void *stream);
-size_t toda_spconv_wgrad_workspace_bytes(int n_out, int kvol, int cin, int cout);
+                    int cout, const float *bias, float *y, int precision, void *workspace, size_t workspace_bytes,
+                    void *stream);
+size_t toda_spconv_wgrad_workspace_bytes(int n_in, int n_out, int kvol, int cin, int cout, int precision);
 int toda_spconv_wgrad(const float *x, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *dy,
                       int cout, float *dw_param, void *workspace, size_t workspace_bytes, int precision, void *stream);
 

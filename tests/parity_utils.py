@@ -184,8 +184,14 @@ def run_smoke():
     assert np.array_equal(*[sort_rows(r["enc_features"], r["enc_indices"])[1] for r in (rg, ro)])
     assert_close(rg["spatial_features"], ro["spatial_features"], what="spatial_features")
     assert_close(rg["dvoxel_features"], ro["dvoxel_features"], rtol=1e-3, what="d voxel_features")
+    gmax = max(float(np.abs(g).max()) for g in ro["grads"].values())
     for name, g in ro["grads"].items():
-        assert_close(rg["grads"][name], g, rtol=1e-3, atol_scale=1e-4, what="grad " + name)
+        # conv biases in front of a BatchNorm have a mathematically zero gradient (rounding noise ~1e-7 of the
+        # weight gradients): compare those on the global gradient scale
+        if name.endswith(".bias") and float(np.abs(g).max()) < 1e-5 * gmax:
+            assert float(np.abs(rg["grads"][name]).max()) < 1e-5 * gmax, name
+        else:
+            assert_close(rg["grads"][name], g, rtol=1e-3, atol_scale=1e-4, what="grad " + name)
 
 
 def _oracle_hc(bd):

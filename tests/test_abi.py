@@ -40,7 +40,7 @@ def test_size_queries_work_without_a_gpu(built):
     assert lib.toda_index_bytes(4, 41, 1440, 1440) > 4 * 41 * 1440 * 1440 // 8
     assert lib.toda_index_bytes(0, 41, 1440, 1440) == 0
     assert lib.toda_bn_workspace_bytes(128) > 0
-    assert lib.toda_spconv_wgrad_workspace_bytes(100000, 27, 64, 64) >= 27 * 64 * 64 * 4
+    assert lib.toda_spconv_wgrad_workspace_bytes(100000, 100000, 27, 64, 64, 0) >= 27 * 64 * 64 * 4
     grid = built.ints([1440, 1440, 40])
     assert lib.toda_voxelize_workspace_bytes(1200000, 4, grid, 10, 120000) > 0
 
@@ -49,7 +49,7 @@ def test_argument_errors_are_reported_not_ignored(built):
     lib = built.lib()
     rc = lib.toda_mean_vfe_fwd(None, None, 0, 10, 0, 5, None, None)
     assert rc == -1 and b"mean_vfe_fwd" in lib.toda_last_error()
-    rc = lib.toda_spconv_fwd(None, 0, 0, None, 5, 27, None, 16, None, None, 0, None)
+    rc = lib.toda_spconv_fwd(None, 0, 0, None, 5, 27, None, 16, None, None, 0, None, 0, None)
     assert rc == -1
 
 

@@ -288,7 +288,9 @@ def test_backbone_vs_reference_golden(cls, fname):
     PU.assert_close(r["dvoxel_features"], g["train_dvoxel_features"], rtol=1e-3, what="d voxel_features")
     names = [str(n) for n in g["grad_names"]]
     norms = np.array([np.linalg.norm(r["grads"][n].astype(np.float64)) for n in names])
-    np.testing.assert_allclose(norms, g["grad_norms"], rtol=2e-3, atol=1e-5)
+    # conv biases feeding a BatchNorm have a mathematically zero gradient: their golden norms (~1e-3 next to
+    # ~1e4 for the weights) are rounding noise, hence the absolute floor
+    np.testing.assert_allclose(norms, g["grad_norms"], rtol=2e-3, atol=1e-6 * float(g["grad_norms"].max()))
     PU.assert_close(r["grads"]["conv_input.0.weight"], g["grad_conv_input_weight"], rtol=1e-3, atol_scale=1e-4, what="wgrad in")
     PU.assert_close(r["grads"]["conv_out.0.weight"], g["grad_conv_out_weight"], rtol=1e-3, atol_scale=1e-4, what="wgrad out")
     PU.assert_close(net.conv_input[1].running_mean.cpu().numpy(), g["running_mean_conv_input"], what="running_mean")

@@ -1,0 +1,108 @@
+"""bf16 tensor-core (tcgen05) convolution path: parity against the CPU oracle evaluated on the SAME
+bf16-rounded operands (then only the fp32 accumulation order differs: rtol 1e-4), plus the stated
+end-to-end bf16 tolerance against the pure-fp32 oracle."""
+import numpy as np
+import pytest
+import torch
+
+from tests import parity_utils as PU
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+BF16_E2E_RTOL = 5e-2     # stated bf16 tolerance vs the fp32 oracle: relative L2 error of the encoder output
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.mark.parametrize("subm,cin,cout,k,s,p", [
+    (True, 16, 16, 3, 1, 1), (True, 32, 32, 3, 1, 1), (True, 64, 64, 3, 1, 1), (True, 128, 128, 3, 1, 1),
+    (False, 16, 32, 3, 2, 1), (False, 32, 64, 3, 2, 1), (False, 64, 128, 3, 2, (0, 1, 1)),
+    (False, 128, 128, (3, 1, 1), (2, 1, 1), 0), (False, 64, 64, 3, 2, (0, 1, 1))])
+def test_tc_conv_fwd_dgrad_vs_bf16_oracle(subm, cin, cout, k, s, p):
+    from oracle import spconv_oracle as S
+    from toda_b200.spconv_compat import pytorch as G
+    torch.manual_seed(0)
+    mk = (lambda sp: sp.SubMConv3d(cin, cout, k, padding=p, bias=True, indice_key="a")) if subm else \
+        (lambda sp: sp.SparseConv3d(cin, cout, k, stride=s, padding=p, bias=True, indice_key="a"))
+    a, b = mk(S), mk(G)
+    with torch.no_grad():
+        a.weight.copy_(bf16_round(a.weight))
+    b.load_state_dict(a.state_dict())
+    b = b.to(DEV)
+    shape, n, batch = [9, 24, 31], 3000, 2
+    feats, idx = PU.random_sparse(7, batch, shape, n, cin)
+    feats = bf16_round(torch.from_numpy(feats))
+    fa = feats.clone().requires_grad_(True)
+    fb = feats.clone().to(DEV).requires_grad_(True)
+    ya = a(S.SparseConvTensor(fa, torch.from_numpy(idx), shape, batch))
+    G.set_conv_precision("bf16")
+    try:
+        yb = b(G.SparseConvTensor(fb, torch.from_numpy(idx).to(DEV), shape, batch))
+        assert np.array_equal(yb.indices.cpu().numpy(), ya.indices.numpy())
+        PU.assert_close(yb.features.detach().cpu().numpy(), ya.features.detach().numpy(), what="tc fwd")
+        g = bf16_round(torch.randn(ya.features.shape, generator=torch.Generator().manual_seed(3)))
+        ya.features.backward(g)
+        yb.features.backward(g.to(DEV))
+    finally:
+        G.set_conv_precision("fp32")
+    PU.assert_close(fb.grad.cpu().numpy(), fa.grad.numpy(), what="tc dgrad")
+    PU.assert_close(b.weight.grad.cpu().numpy(), a.weight.grad.numpy(), what="wgrad")
+    PU.assert_close(b.bias.grad.cpu().numpy(), a.bias.grad.numpy(), what="bias grad")
+
+
+def test_tc_ragged_tail_and_missing_neighbours():
+    """n_out not a multiple of the 128-row tile; isolated voxels (all 26 neighbours missing)."""
+    from oracle import spconv_oracle as S
+    from toda_b200.spconv_compat import pytorch as G
+    torch.manual_seed(1)
+    a = S.SubMConv3d(32, 64, 3, padding=1, bias=False, indice_key="a")
+    with torch.no_grad():
+        a.weight.copy_(bf16_round(a.weight))
+    b = G.SubMConv3d(32, 64, 3, padding=1, bias=False, indice_key="a")
+    b.load_state_dict(a.state_dict())
+    b = b.to(DEV)
+    for n in (1, 127, 129, 1000):
+        feats, idx = PU.random_sparse(n, 1, [40, 50, 60], n, 32)
+        feats = bf16_round(torch.from_numpy(feats))
+        ya = a(S.SparseConvTensor(feats, torch.from_numpy(idx), [40, 50, 60], 1))
+        G.set_conv_precision("bf16")
+        try:
+            yb = b(G.SparseConvTensor(feats.to(DEV), torch.from_numpy(idx).to(DEV), [40, 50, 60], 1))
+        finally:
+            G.set_conv_precision("fp32")
+        PU.assert_close(yb.features.detach().cpu().numpy(), ya.features.detach().numpy(), what=f"tc n={n}")
+
+
+def test_backbone_bf16_end_to_end_tolerance():
+    """VoxelResBackBone8x on the golden crop in bf16 mode vs the fp32 reference golden: stated tolerance."""
+    import toda_b200.pcdet_plugin as P
+    from toda_b200.spconv_compat import pytorch as G
+    g = PU.load_golden("backbone_res.npz")
+    twin, net = PU.build_pair("VoxelResBackBone8x", 5, g["grid_size"], seed=int(g["seed"]))
+    hc = P.HeightCompression(PU.Cfg(NUM_BEV_FEATURES=256))
+    vf = torch.from_numpy(g["voxel_features"]).to(DEV)
+    vc = torch.from_numpy(g["voxel_coords"]).float().to(DEV)
+    cot = torch.randn(tuple(g["bev_shape"]), generator=torch.Generator().manual_seed(int(g["seed"])))
+    G.set_conv_precision("bf16")
+    try:
+        r = PU.run_backbone(net, hc, vf, vc, 2, cot=cot, train=True)
+    finally:
+        G.set_conv_precision("fp32")
+    f_sorted, i_sorted = PU.sort_rows(r["enc_features"], r["enc_indices"])
+    assert np.array_equal(i_sorted, g["train_enc_indices"])           # geometry is precision-independent: bit-exact
+    def rel_l2(a, b):
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+    # stated bf16 tolerance (21 layers of bf16-rounded operands, fp32 accumulate, batch-statistics BN):
+    # relative L2 error <= 5e-2 for activations, <= 1.5e-1 for the gradient that crossed the whole network backwards
+    e_feat = rel_l2(f_sorted, g["train_enc_features"])
+    e_grad = rel_l2(r["dvoxel_features"], g["train_dvoxel_features"])
+    print("bf16 end-to-end rel-L2: features %.3e, d voxel_features %.3e" % (e_feat, e_grad))
+    assert e_feat <= BF16_E2E_RTOL, e_feat
+    assert e_grad <= 3 * BF16_E2E_RTOL, e_grad
+    names = [str(n) for n in g["grad_names"]]
+    norms = np.array([np.linalg.norm(r["grads"][n].astype(np.float64)) for n in names])
+    big = g["grad_norms"] > 1e-3 * g["grad_norms"].max()
+    np.testing.assert_allclose(norms[big], g["grad_norms"][big], rtol=3 * BF16_E2E_RTOL)

@@ -6,10 +6,13 @@
 #include "common.cuh"
 
 int conv_tc_fwd(const float *x, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *w, int cout,
-                const float *bias, float *y, cudaStream_t st);
+                const float *bias, float *y, void *workspace, size_t workspace_bytes, cudaStream_t st);
+size_t conv_tc_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol);
 int conv_tc_wgrad(const float *x, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *dy, int cout,
                   float *dw_param, void *workspace, size_t workspace_bytes, cudaStream_t st);
 bool conv_tc_supported(int cin, int cout);
+bool conv_tc_wgrad_supported(int cin, int cout);
+size_t conv_tc_wgrad_workspace_bytes(int n_in, int n_out, int kvol, int cin, int cout);
 
 namespace {
 
@@ -236,20 +239,24 @@ extern "C" int toda_weight_repack(const float *w_param, int kvol, int cin, int c
     return TODA_OK;
 }
 
+extern "C" size_t toda_spconv_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol, int precision) {
+    if (precision == TODA_CONV_BF16 && n_in >= 0 && cin > 0 && cout > 0 && kvol > 0)
+        return conv_tc_fwd_workspace_bytes(n_in, cin, cout, kvol);
+    return 0;
+}
+
 extern "C" int toda_spconv_fwd(const float *x, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
-                               const float *w, int cout, const float *bias, float *y, int precision, void *stream) {
+                               const float *w, int cout, const float *bias, float *y, int precision, void *workspace,
+                               size_t workspace_bytes, void *stream) {
     TODA_CHECK_ARG(n_in >= 0 && n_out >= 0 && cin > 0 && cout > 0 && kvol > 0, "spconv_fwd: bad sizes");
     if (n_out == 0) return TODA_OK;
     TODA_CHECK_ARG(x && nbr && w && y, "spconv_fwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    if (precision == TODA_CONV_BF16) {
-        if (!conv_tc_supported(cin, cout)) {
-            toda_set_error("spconv_fwd: bf16 tensor-core path does not support cin=%d cout=%d", cin, cout);
-            return TODA_ERR_UNSUPPORTED;
-        }
-        return conv_tc_fwd(x, n_in, cin, nbr, n_out, kvol, w, cout, bias, y, st);
-    }
-    TODA_CHECK_ARG(precision == TODA_CONV_FP32, "spconv_fwd: unknown precision %d", precision);
+    TODA_CHECK_ARG(precision == TODA_CONV_FP32 || precision == TODA_CONV_BF16, "spconv_fwd: unknown precision %d", precision);
+    // kernel selection by shape: the tensor-core kernel needs Cin % 16 == 0 (UMMA K) and Cout in {16,32,64,128};
+    // the 4/5-channel input layer (conv_input) runs on the FFMA kernel in either mode.
+    if (precision == TODA_CONV_BF16 && conv_tc_supported(cin, cout))
+        return conv_tc_fwd(x, n_in, cin, nbr, n_out, kvol, w, cout, bias, y, workspace, workspace_bytes, st);
     if (cout <= 16) {
         dim3 grid(ceil_div(n_out, 256), ceil_div(cout, 16));
         conv_fwd_f32_kernel<256, 16><<<grid, kThreads, 0, st>>>(x, cin, nbr, n_out, kvol, w, cout, bias, y);
@@ -264,8 +271,10 @@ extern "C" int toda_spconv_fwd(const float *x, int n_in, int cin, const int32_t 
     return TODA_OK;
 }
 
-extern "C" size_t toda_spconv_wgrad_workspace_bytes(int n_out, int kvol, int cin, int cout) {
-    if (n_out < 0 || kvol <= 0 || cin <= 0 || cout <= 0) return 0;
+extern "C" size_t toda_spconv_wgrad_workspace_bytes(int n_in, int n_out, int kvol, int cin, int cout, int precision) {
+    if (n_in < 0 || n_out < 0 || kvol <= 0 || cin <= 0 || cout <= 0) return 0;
+    if (precision == TODA_CONV_BF16 && conv_tc_wgrad_supported(cin, cout))
+        return conv_tc_wgrad_workspace_bytes(n_in, n_out, kvol, cin, cout);
     int splits = wgrad_splits(n_out, kvol, cin, cout);
     return align_up((size_t)splits * kvol * cin * cout * sizeof(float), 256);
 }
@@ -281,14 +290,9 @@ extern "C" int toda_spconv_wgrad(const float *x, int n_in, int cin, const int32_
         return TODA_OK;
     }
     TODA_CHECK_ARG(x && nbr && dy && workspace, "spconv_wgrad: null pointer");
-    if (precision == TODA_CONV_BF16) {
-        if (!conv_tc_supported(cin, cout)) {
-            toda_set_error("spconv_wgrad: bf16 tensor-core path does not support cin=%d cout=%d", cin, cout);
-            return TODA_ERR_UNSUPPORTED;
-        }
+    TODA_CHECK_ARG(precision == TODA_CONV_FP32 || precision == TODA_CONV_BF16, "spconv_wgrad: unknown precision %d", precision);
+    if (precision == TODA_CONV_BF16 && conv_tc_wgrad_supported(cin, cout))
         return conv_tc_wgrad(x, n_in, cin, nbr, n_out, kvol, dy, cout, dw_param, workspace, workspace_bytes, st);
-    }
-    TODA_CHECK_ARG(precision == TODA_CONV_FP32, "spconv_wgrad: unknown precision %d", precision);
     int splits = wgrad_splits(n_out, kvol, cin, cout);
     size_t need = (size_t)splits * kvol * cin * cout * sizeof(float);
     if (workspace_bytes < need) {

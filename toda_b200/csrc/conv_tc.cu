@@ -1,14 +1,556 @@
-// K5/K7 bf16 tensor-core path (tcgen05 + TMEM).  Placeholder until the tcgen05 kernels land:
-// reports "unsupported" so callers fail loudly rather than silently taking another path.
+// K5/K6 sparse convolution on the 5th-generation tensor cores (TODA_CONV_BF16):
+//   y[o, :] = bias + sum_{k, ci} x[nbr[k,o], ci] * w[k, ci, :]        bf16 operands, fp32 accumulate in TMEM
+//
+// Implicit GEMM, output-stationary.  One CTA owns 128 output rows (UMMA M = 128, cta_group::1, which runs the
+// tensor pipe at full rate) and all Cout columns (UMMA N = Cout).  The reduction dimension is the flattened
+// (kernel offset, input channel) axis, K = kvol*Cin, walked in chunks of 64 bf16 = one 128-byte swizzle row:
+//   A chunk [128 rows x 64]  : gathered -- for every row the neighbour named by the table, 16 bytes per
+//                              cp.async, written straight into the SWIZZLE_128B K-major layout tcgen05 reads;
+//                              missing neighbours (-1) are zero-filled by the same instruction (src-size 0)
+//   B chunk [Cout rows x 64] : the weights, K-major ([Cout][kvol*Cin] bf16), same layout
+// Warps 0-3 (128 threads) produce both chunks into a ring of shared-memory stages and later run the epilogue;
+// warp 4 allocates TMEM and one of its threads issues the tcgen05.mma stream.  Stage hand-off is by mbarrier:
+// full[s] completes when the 128 producers' cp.asyncs have landed (cp.async.mbarrier.arrive.noinc), empty[s]
+// when the MMAs that read the stage have retired (tcgen05.commit).  Epilogue: tcgen05.ld (32 lanes x 32 bit),
+// + bias, fp32 rows to global.
+//
+// No scatter and no atomics: every output row is written once.  dgrad is the same kernel on the
+// input-stationary table with transposed weights.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
-bool conv_tc_supported(int cin, int cout) { (void)cin; (void)cout; return false; }
+namespace {
 
-int conv_tc_fwd(const float *, int, int, const int32_t *, int, int, const float *, int, const float *, float *, cudaStream_t) {
-    toda_set_error("conv_tc_fwd: not built");
-    return TODA_ERR_UNSUPPORTED;
+constexpr int kTileM = 128;
+constexpr int kChunkK = 64;                       // bf16 elements per K chunk (128 bytes)
+constexpr int kStages = 3;
+constexpr int kProducers = 128;
+constexpr int kThreadsTC = kProducers + 32;
+constexpr int kABytes = kTileM * kChunkK * 2;     // 16 KB
+constexpr int kBBytesMax = 128 * kChunkK * 2;     // 16 KB (Cout <= 128)
+constexpr int kStageBytes = kABytes + kBBytesMax;
+constexpr int kSmemTC = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-int conv_tc_wgrad(const float *, int, int, const int32_t *, int, int, const float *, int, float *, void *, size_t, cudaStream_t) {
-    toda_set_error("conv_tc_wgrad: not built");
-    return TODA_ERR_UNSUPPORTED;
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    uint32_t spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!done && ++spins > (1u << 24)) __trap();   // a lost arrival must not hang the GPU box
+    }
+}
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (1 for swizzled K-major) |
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B between 8-row groups) | [46,48) version = 1 (sm_100) |
+//   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, M=128, N=n
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// byte offset of 16-byte piece `p` of row `r` inside a [rows][64 bf16] SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t sw128_offset(int r, int p) { return (uint32_t)(r * 128 + ((p ^ (r & 7)) << 4)); }
+
+template <int COUT>
+__global__ void __launch_bounds__(kThreadsTC, 1) conv_tc_fwd_kernel(const __nv_bfloat16 *__restrict__ xb, int cin,
+                                                                    const int *__restrict__ nbr, int n_out, int kvol,
+                                                                    const __nv_bfloat16 *__restrict__ wb /*[COUT][kvol*cin]*/,
+                                                                    const float *__restrict__ bias, float *__restrict__ y) {
+    static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 128, "UMMA N");
+    constexpr int kTmemCols = COUT < 32 ? 32 : COUT;   // power of two >= 32
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t bar_base = base + kStages * kStageBytes;
+    const uint32_t full_bar = bar_base, empty_bar = bar_base + 8 * kStages, accum_bar = bar_base + 16 * kStages;
+    const uint32_t tmem_slot = bar_base + 16 * kStages + 8;
+    volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int row0 = blockIdx.x * kTileM;
+    const int ktot = kvol * cin;
+    const int nchunks = (ktot + kChunkK - 1) / kChunkK;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar + 8 * s, kProducers);
+            mbar_init(empty_bar + 8 * s, 1);
+        }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp < 4) {
+        // ------------------------------------------------------------------ producers
+        const int p = tid & 7;          // 16-byte piece of the 128-byte chunk row
+        const int rbase = tid >> 3;     // rows rbase + 16*i
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % kStages, use = c / kStages;
+            if (use > 0) mbar_wait(empty_bar + 8 * s, (use - 1) & 1);
+            const uint32_t a_tile = base + s * kStageBytes, b_tile = a_tile + kABytes;
+            const int kk = c * kChunkK + p * 8;          // position of this thread's piece on the flattened K axis
+            const bool k_ok = kk < ktot;
+            const int k = k_ok ? kk / cin : 0, ci = k_ok ? kk % cin : 0;
+            int src[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int r = row0 + rbase + 16 * i;
+                src[i] = (k_ok && r < n_out) ? __ldg(nbr + (size_t)k * n_out + r) : -1;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = rbase + 16 * i;
+                const bool ok = src[i] >= 0;
+                const __nv_bfloat16 *g = ok ? xb + (size_t)src[i] * cin + ci : xb;
+                cp_async_16(a_tile + sw128_offset(r, p), g, ok ? 16u : 0u);
+            }
+#pragma unroll
+            for (int j = 0; j < COUT / 16; ++j) {
+                const int r = rbase + 16 * j;
+                const __nv_bfloat16 *g = k_ok ? wb + (size_t)r * ktot + kk : wb;
+                cp_async_16(b_tile + sw128_offset(r, p), g, k_ok ? 16u : 0u);
+            }
+            cp_async_arrive_noinc(full_bar + 8 * s);
+        }
+        // ------------------------------------------------------------------ epilogue (same four warps)
+        mbar_wait(accum_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = row0 + warp * 32 + (tid & 31);       // TMEM lane = tile row; warp w owns lanes 32w..32w+31
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+        for (int n0 = 0; n0 < COUT; n0 += 16) {
+            uint32_t v[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(taddr + n0));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < n_out) {
+                float4 *dst = (float4 *)(y + (size_t)row * COUT + n0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float4 o;
+                    o.x = __uint_as_float(v[4 * q + 0]) + (bias ? __ldg(bias + n0 + 4 * q + 0) : 0.f);
+                    o.y = __uint_as_float(v[4 * q + 1]) + (bias ? __ldg(bias + n0 + 4 * q + 1) : 0.f);
+                    o.z = __uint_as_float(v[4 * q + 2]) + (bias ? __ldg(bias + n0 + 4 * q + 2) : 0.f);
+                    o.w = __uint_as_float(v[4 * q + 3]) + (bias ? __ldg(bias + n0 + 4 * q + 3) : 0.f);
+                    dst[q] = o;
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else {
+        // ------------------------------------------------------------------ MMA issuer (one thread of warp 4)
+        if ((tid & 31) == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(kTileM, COUT);
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % kStages, use = c / kStages;
+                mbar_wait(full_bar + 8 * s, use & 1);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async writes -> async-proxy reads
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_tile = base + s * kStageBytes, b_tile = a_tile + kABytes;
+                const int ksteps = min(kChunkK, ktot - c * kChunkK) / 16;     // UMMA K = 16 bf16 = 32 bytes
+                for (int j = 0; j < ksteps; ++j) {
+                    uint64_t ad = make_desc_k_sw128(a_tile + j * 32);
+                    uint64_t bd = make_desc_k_sw128(b_tile + j * 32);
+                    umma_bf16(tmem_base, ad, bd, idesc, (c | j) != 0);
+                }
+                umma_commit(empty_bar + 8 * s);        // stage reusable once these MMAs have read it
+            }
+            umma_commit(accum_bar);                    // accumulator complete
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
+__global__ void f32_to_bf16_kernel(const float *__restrict__ in, long long n4, __nv_bfloat16 *__restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 v = __ldg((const float4 *)in + i);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 o;
+        o.x = *(uint32_t *)&lo;
+        o.y = *(uint32_t *)&hi;
+        ((uint2 *)out)[i] = o;
+    }
+}
+
+// w [kvol][cin][cout] fp32  ->  wb [cout][kvol*cin] bf16 (K-major rows for the B operand)
+__global__ void weight_to_kmajor_bf16_kernel(const float *__restrict__ w, int kvol, int cin, int cout,
+                                             __nv_bfloat16 *__restrict__ wb) {
+    size_t per = (size_t)kvol * cin * cout;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < per; e += (size_t)gridDim.x * blockDim.x) {
+        size_t kc = e % ((size_t)kvol * cin);
+        int co = (int)(e / ((size_t)kvol * cin));
+        wb[e] = __float2bfloat16_rn(__ldg(w + kc * cout + co));
+    }
+}
+
+}  // namespace
+
+bool conv_tc_supported(int cin, int cout) {
+    return cin % 16 == 0 && cin >= 16 && cin <= 128 && (cout == 16 || cout == 32 || cout == 64 || cout == 128);
+}
+
+size_t conv_tc_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol) {
+    return align_up((size_t)n_in * cin * 2, 256) + align_up((size_t)kvol * cin * cout * 2, 256) + 256;
+}
+
+int conv_tc_fwd(const float *x, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *w, int cout,
+                const float *bias, float *y, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+    size_t need = conv_tc_fwd_workspace_bytes(n_in, cin, cout, kvol);
+    if (!workspace || workspace_bytes < need) {
+        toda_set_error("spconv_fwd(bf16): workspace %zu < required %zu bytes", workspace_bytes, need);
+        return TODA_ERR_WORKSPACE;
+    }
+    __nv_bfloat16 *xb = (__nv_bfloat16 *)workspace;
+    __nv_bfloat16 *wb = (__nv_bfloat16 *)((char *)workspace + align_up((size_t)n_in * cin * 2, 256));
+    long long n4 = (long long)n_in * cin / 4;
+    if (n4 > 0) {
+        f32_to_bf16_kernel<<<wave_grid(n4, 256), 256, 0, st>>>(x, n4, xb);
+        TODA_LAUNCH_OK();
+    }
+    weight_to_kmajor_bf16_kernel<<<wave_grid((int64_t)kvol * cin * cout, 256), 256, 0, st>>>(w, kvol, cin, cout, wb);
+    TODA_LAUNCH_OK();
+    int grid = ceil_div(n_out, kTileM);
+#define LAUNCH_TC(CO)                                                                                              \
+    do {                                                                                                           \
+        TODA_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTC)); \
+        conv_tc_fwd_kernel<CO><<<grid, kThreadsTC, kSmemTC, st>>>(xb, cin, nbr, n_out, kvol, wb, bias, y);          \
+    } while (0)
+    switch (cout) {
+        case 16: LAUNCH_TC(16); break;
+        case 32: LAUNCH_TC(32); break;
+        case 64: LAUNCH_TC(64); break;
+        case 128: LAUNCH_TC(128); break;
+        default: toda_set_error("conv_tc_fwd: unsupported cout %d", cout); return TODA_ERR_UNSUPPORTED;
+    }
+#undef LAUNCH_TC
+    TODA_LAUNCH_OK();
+    return TODA_OK;
+}
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+// K7 weight gradient on tensor cores:  dw[k][ci][co] = sum_o x[nbr[k,o], ci] * dy[o, co]
+// The reduction runs over output rows, so both operands are "MN-major" for tcgen05: shared-memory tiles are
+// [row][channel] with channels contiguous (exactly how rows are gathered), rows being the UMMA K dimension.
+//   A tile [64 rows][128 M-slots]: M = (128/Cin) kernel offsets x Cin channels -- small-channel layers stack several
+//                                  offsets on the M axis so that every MMA is a full M=128 instruction
+//   B tile [64 rows][NPAD]       : dy rows (NPAD = max(64, Cout); columns >= Cout are zero)
+// One "pass" = one group of 128/Cin offsets = one [128 x NPAD] fp32 accumulator in TMEM; a CTA keeps up to
+// 512/NPAD passes resident and owns a slice of the rows (split-K over rows); partial results go to a workspace
+// and are reduced in a fixed order (deterministic) into the parameter layout.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kRowsW = 64;                         // reduction rows per stage
+constexpr int kStagesW = 3;
+constexpr int kStageBytesW = 2 * kRowsW * 128 + 2 * kRowsW * 128;   // A: two 64-wide M blocks; B: up to two N blocks
+constexpr int kSmemW = kStagesW * kStageBytesW + 1024 + 256;
+
+// MN-major SWIZZLE_128B descriptor: 64 channels (128 B) contiguous, next 64-channel block at `lbo` bytes,
+// groups of 8 rows 1024 B apart.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+template <int CIN, int NPAD>
+__global__ void __launch_bounds__(kThreadsTC, 1) conv_tc_wgrad_kernel(const __nv_bfloat16 *__restrict__ xb,
+                                                                      const int *__restrict__ nbr, int n_out, int kvol,
+                                                                      const __nv_bfloat16 *__restrict__ dyb, int cout,
+                                                                      int rows_per_split, int passes_per_cta,
+                                                                      float *__restrict__ partial) {
+    constexpr int kOffsPerPass = 128 / CIN;
+    constexpr int kMaxPasses = 512 / NPAD;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = base + kStagesW * kStageBytesW;
+    const uint32_t full_bar = bar_base, empty_bar = bar_base + 8 * kStagesW, accum_bar = bar_base + 16 * kStagesW;
+    const uint32_t tmem_slot = bar_base + 16 * kStagesW + 8;
+    volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int split = blockIdx.x, group = blockIdx.y;
+    const int total_passes = (kvol + kOffsPerPass - 1) / kOffsPerPass;
+    const int pass0 = group * passes_per_cta;
+    const int npass = min(passes_per_cta, total_passes - pass0);
+    const int r_begin = split * rows_per_split;
+    const int r_end = min(n_out, r_begin + rows_per_split);
+    const int nchunks = r_end > r_begin ? (r_end - r_begin + kRowsW - 1) / kRowsW : 0;
+    const int nitems = nchunks * npass;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStagesW; ++s) {
+            mbar_init(full_bar + 8 * s, kProducers);
+            mbar_init(empty_bar + 8 * s, 1);
+        }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // TMEM columns: one [128 x NPAD] accumulator per resident pass, rounded up to a power of two
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < passes_per_cta * NPAD) tmem_cols <<= 1;
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp < 4) {
+        const int p = tid & 7, rr = tid >> 3;           // 16-byte piece, row lane (rows rr + 16*i)
+        for (int it = 0; it < nitems; ++it) {
+            const int s = it % kStagesW, use = it / kStagesW;
+            if (use > 0) mbar_wait(empty_bar + 8 * s, (use - 1) & 1);
+            const int rc = it / npass, ps = it - rc * npass;
+            const int row_base = r_begin + rc * kRowsW;
+            const uint32_t a_tile = base + s * kStageBytesW, b_tile = a_tile + 2 * kRowsW * 128;
+            // A: M slot m = mb*64 + p*8 -> kernel offset and channel of this thread's piece
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) {
+                const int m = mb * 64 + p * 8;
+                const int k = (pass0 + ps) * kOffsPerPass + m / CIN, ci = m % CIN;
+                const bool k_ok = k < kvol;
+                int src[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    int r = row_base + rr + 16 * i;
+                    src[i] = (k_ok && r < r_end) ? __ldg(nbr + (size_t)k * n_out + r) : -1;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = rr + 16 * i;
+                    const bool ok = src[i] >= 0;
+                    const __nv_bfloat16 *g = ok ? xb + (size_t)src[i] * CIN + ci : xb;
+                    cp_async_16(a_tile + mb * (kRowsW * 128) + sw128_offset(r, p), g, ok ? 16u : 0u);
+                }
+            }
+#pragma unroll
+            for (int nb = 0; nb < NPAD / 64; ++nb) {
+                const int co = nb * 64 + p * 8;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = rr + 16 * i;
+                    const bool ok = (row_base + r < r_end) && co < cout;
+                    const __nv_bfloat16 *g = ok ? dyb + (size_t)(row_base + r) * cout + co : dyb;
+                    cp_async_16(b_tile + nb * (kRowsW * 128) + sw128_offset(r, p), g, ok ? 16u : 0u);
+                }
+            }
+            cp_async_arrive_noinc(full_bar + 8 * s);
+        }
+        // epilogue: TMEM lane = M slot (offset, ci); this thread owns one (k, ci) row of every pass
+        if (nitems > 0) {
+            mbar_wait(accum_bar, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const int m = warp * 32 + (tid & 31);
+        for (int ps = 0; ps < npass; ++ps) {
+            const int k = (pass0 + ps) * kOffsPerPass + m / CIN, ci = m % CIN;
+            float *dst = partial + (((size_t)split * kvol + k) * CIN + ci) * cout;
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + ps * NPAD;
+            for (int n0 = 0; n0 < cout; n0 += 16) {
+                uint32_t v[16];
+                if (nitems > 0) {
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                        : "r"(taddr + n0));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) v[q] = 0u;      // this split has no rows: its partial is zero
+                }
+                if (k < kvol) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        *(float4 *)(dst + n0 + 4 * q) = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                                    __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else {
+        if ((tid & 31) == 0 && nitems > 0) {
+            // D = A(MN-major) x B(MN-major): bits 15 / 16 of the instruction descriptor select MN-major operands
+            constexpr uint32_t idesc = make_idesc_bf16(128, NPAD) | (1u << 15) | (1u << 16);
+            for (int it = 0; it < nitems; ++it) {
+                const int s = it % kStagesW, use = it / kStagesW;
+                mbar_wait(full_bar + 8 * s, use & 1);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int rc = it / npass, ps = it - rc * npass;
+                const uint32_t a_tile = base + s * kStageBytesW, b_tile = a_tile + 2 * kRowsW * 128;
+#pragma unroll
+                for (int j = 0; j < kRowsW / 16; ++j) {     // UMMA K = 16 rows = 2 swizzle atoms of 8 rows
+                    uint64_t ad = make_desc_mn_sw128(a_tile + j * 2048, kRowsW * 128);
+                    uint64_t bd = make_desc_mn_sw128(b_tile + j * 2048, kRowsW * 128);
+                    umma_bf16(tmem_base + ps * NPAD, ad, bd, idesc, (rc | j) != 0);
+                }
+                umma_commit(empty_bar + 8 * s);
+            }
+            umma_commit(accum_bar);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+    (void)kMaxPasses;
+}
+
+// fixed-order reduction over splits into the parameter layout (Cout, kvol, Cin)
+__global__ void wgrad_tc_reduce_kernel(const float *__restrict__ partial, int splits, int kvol, int cin, int cout,
+                                       float *__restrict__ dw_param) {
+    size_t per = (size_t)kvol * cin * cout;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < per; e += (size_t)gridDim.x * blockDim.x) {
+        int ci = (int)(e % cin);
+        size_t t = e / cin;
+        int k = (int)(t % kvol);
+        int co = (int)(t / kvol);
+        size_t src = ((size_t)k * cin + ci) * cout + co;
+        float s = 0.f;
+        for (int sp = 0; sp < splits; ++sp) s += partial[sp * per + src];
+        dw_param[e] = s;
+    }
+}
+
+struct WgradPlan {
+    int passes_per_cta, groups, splits, rows_per_split;
+    size_t xb_bytes, dyb_bytes, partial_bytes;
+};
+
+WgradPlan wgrad_plan(int n_in, int n_out, int kvol, int cin, int cout) {
+    WgradPlan p;
+    int npad = cout <= 64 ? 64 : 128;
+    int offs = 128 / cin;
+    int total_passes = (kvol + offs - 1) / offs;
+    p.passes_per_cta = total_passes < 512 / npad ? total_passes : 512 / npad;
+    p.groups = (total_passes + p.passes_per_cta - 1) / p.passes_per_cta;
+    int want = (2 * kNumSMs + p.groups - 1) / p.groups;
+    int max_by_rows = (n_out + 4 * kRowsW - 1) / (4 * kRowsW);
+    p.splits = want < max_by_rows ? want : max_by_rows;
+    if (p.splits < 1) p.splits = 1;
+    int rps = (n_out + p.splits - 1) / p.splits;
+    p.rows_per_split = (rps + kRowsW - 1) / kRowsW * kRowsW;
+    if (p.rows_per_split < kRowsW) p.rows_per_split = kRowsW;
+    p.xb_bytes = align_up((size_t)n_in * cin * 2 + 16, 256);
+    p.dyb_bytes = align_up((size_t)n_out * cout * 2 + 16, 256);
+    p.partial_bytes = align_up((size_t)p.splits * kvol * cin * cout * 4, 256);
+    return p;
+}
+
+}  // namespace
+
+bool conv_tc_wgrad_supported(int cin, int cout) {
+    return (cin == 16 || cin == 32 || cin == 64 || cin == 128) && (cout == 16 || cout == 32 || cout == 64 || cout == 128);
+}
+
+size_t conv_tc_wgrad_workspace_bytes(int n_in, int n_out, int kvol, int cin, int cout) {
+    WgradPlan p = wgrad_plan(n_in, n_out, kvol, cin, cout);
+    return p.xb_bytes + p.dyb_bytes + p.partial_bytes + 256;
+}
+
+int conv_tc_wgrad(const float *x, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *dy, int cout,
+                  float *dw_param, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+    WgradPlan p = wgrad_plan(n_in, n_out, kvol, cin, cout);
+    size_t need = p.xb_bytes + p.dyb_bytes + p.partial_bytes;
+    if (!workspace || workspace_bytes < need) {
+        toda_set_error("spconv_wgrad(bf16): workspace %zu < required %zu bytes", workspace_bytes, need);
+        return TODA_ERR_WORKSPACE;
+    }
+    __nv_bfloat16 *xb = (__nv_bfloat16 *)workspace;
+    __nv_bfloat16 *dyb = (__nv_bfloat16 *)((char *)workspace + p.xb_bytes);
+    float *partial = (float *)((char *)workspace + p.xb_bytes + p.dyb_bytes);
+    long long n4 = (long long)n_in * cin / 4;
+    if (n4 > 0) {
+        f32_to_bf16_kernel<<<wave_grid(n4, 256), 256, 0, st>>>(x, n4, xb);
+        TODA_LAUNCH_OK();
+    }
+    n4 = (long long)n_out * cout / 4;
+    f32_to_bf16_kernel<<<wave_grid(n4, 256), 256, 0, st>>>(dy, n4, dyb);
+    TODA_LAUNCH_OK();
+    dim3 grid(p.splits, p.groups);
+#define LAUNCH_W(CI, NP)                                                                                                  \
+    do {                                                                                                                   \
+        TODA_CUDA_OK(cudaFuncSetAttribute(conv_tc_wgrad_kernel<CI, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemW)); \
+        conv_tc_wgrad_kernel<CI, NP><<<grid, kThreadsTC, kSmemW, st>>>(xb, nbr, n_out, kvol, dyb, cout, p.rows_per_split,    \
+                                                                       p.passes_per_cta, partial);                          \
+    } while (0)
+    const bool wide = cout > 64;
+    switch (cin) {
+        case 16: if (wide) LAUNCH_W(16, 128); else LAUNCH_W(16, 64); break;
+        case 32: if (wide) LAUNCH_W(32, 128); else LAUNCH_W(32, 64); break;
+        case 64: if (wide) LAUNCH_W(64, 128); else LAUNCH_W(64, 64); break;
+        case 128: if (wide) LAUNCH_W(128, 128); else LAUNCH_W(128, 64); break;
+        default: toda_set_error("conv_tc_wgrad: unsupported cin %d", cin); return TODA_ERR_UNSUPPORTED;
+    }
+#undef LAUNCH_W
+    TODA_LAUNCH_OK();
+    size_t per = (size_t)kvol * cin * cout;
+    wgrad_tc_reduce_kernel<<<wave_grid(per, 256), 256, 0, st>>>(partial, p.splits, kvol, cin, cout, dw_param);
+    TODA_LAUNCH_OK();
+    return TODA_OK;
 }

@@ -34,6 +34,41 @@ def _count(n):
     _launches += n
 
 
+# optional per-call device timing (bench.py's roofline pass): list of (name, meta, start_event, end_event)
+_prof = None
+
+
+def profile_begin():
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """-> list of dicts {name, ms, **meta}; synchronises."""
+    global _prof
+    rec, _prof = _prof, None
+    torch.cuda.synchronize()
+    return [dict(name=n, ms=a.elapsed_time(b), **m) for (n, m, a, b) in rec]
+
+
+class _timed:
+    def __init__(self, name, **meta):
+        self.name, self.meta = name, meta
+
+    def __enter__(self):
+        if _prof is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _prof is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            _prof.append((self.name, self.meta, self.a, b))
+        return False
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -105,10 +140,11 @@ def voxelize(points, frame_offsets, pc_range, voxel_size, max_points, max_voxels
     coords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
     num = torch.empty((cap,), dtype=torch.int32, device=dev)
     counts = torch.empty((batch + 1,), dtype=torch.int32, device=dev)
-    rc = L.toda_voxelize_hard(_p(points), n, stride, xyz_col, feat_col, f, _p(frame_offsets), batch,
-                              _C.floats(np.asarray(pc_range, dtype=np.float32)),
-                              _C.floats(np.asarray(voxel_size, dtype=np.float32)), grid_c, max_points, max_voxels,
-                              order, _p(voxels), _p(coords), _p(num), _p(counts), _p(ws), ws.numel(), _stream())
+    with _timed("voxelize", n_points=n, batch=batch, K=max_points, F=f):
+        rc = L.toda_voxelize_hard(_p(points), n, stride, xyz_col, feat_col, f, _p(frame_offsets), batch,
+                                  _C.floats(np.asarray(pc_range, dtype=np.float32)),
+                                  _C.floats(np.asarray(voxel_size, dtype=np.float32)), grid_c, max_points, max_voxels,
+                                  order, _p(voxels), _p(coords), _p(num), _p(counts), _p(ws), ws.numel(), _stream())
     _C.check(rc, "toda_voxelize_hard")
     _count(16 if order == ORDER_FIRST_APPEARANCE else 19)
     if trim:
@@ -127,8 +163,9 @@ class _MeanVFE(torch.autograd.Function):
             num_points = _need(num_points, torch.int32, "voxel_num_points")
         num_points = num_points.contiguous()
         out = torch.empty((v, f), dtype=torch.float32, device=voxels.device)
-        _C.check(_C.lib().toda_mean_vfe_fwd(_p(voxels), _p(num_points), int(is_float), v, k, f, _p(out), _stream()),
-                 "toda_mean_vfe_fwd")
+        with _timed("mean_vfe_fwd", V=v, K=k, F=f):
+            _C.check(_C.lib().toda_mean_vfe_fwd(_p(voxels), _p(num_points), int(is_float), v, k, f, _p(out), _stream()),
+                     "toda_mean_vfe_fwd")
         _count(1)
         ctx.save_for_backward(num_points)
         ctx.shape = (v, k, f, is_float)
@@ -215,8 +252,9 @@ class OccupancyIndex:
         dev = self.buf.device
         coords = torch.empty((max(cap, 1), 4), dtype=torch.int32, device=dev)
         n_out = torch.empty((self.batch + 1,), dtype=torch.int32, device=dev)
-        _C.check(_C.lib().toda_index_build(_p(self.buf), *self._dims(), _p(coords), cap, _p(n_out), _stream()),
-                 "toda_index_build")
+        with _timed("index_build", cells=self.batch * self.shape[0] * self.shape[1] * self.shape[2]):
+            _C.check(_C.lib().toda_index_build(_p(self.buf), *self._dims(), _p(coords), cap, _p(n_out), _stream()),
+                     "toda_index_build")
         _count(5)
         self.n = int(n_out[0].item()) if known_n is None else int(known_n)
         self.coords = coords[:self.n]
@@ -278,8 +316,9 @@ def rulebook_subm(index: OccupancyIndex, ksize):
     n = index.n
     kvol = ksize[0] * ksize[1] * ksize[2]
     nbr = torch.empty((kvol, n), dtype=torch.int32, device=index.buf.device)
-    _C.check(_C.lib().toda_rulebook_subm(_p(index.buf), index.batch, *index.shape, _p(index.coords), n, _C.ints(ksize),
-                                         _p(nbr), _stream()), "toda_rulebook_subm")
+    with _timed("rulebook_subm", n=n, kvol=kvol):
+        _C.check(_C.lib().toda_rulebook_subm(_p(index.buf), index.batch, *index.shape, _p(index.coords), n, _C.ints(ksize),
+                                             _p(nbr), _stream()), "toda_rulebook_subm")
     _count(1)
     return Rulebook(True, list(ksize), [1, 1, 1], [k // 2 for k in ksize], index.shape, index.shape, n, n, index.coords,
                     nbr, None)
@@ -302,10 +341,11 @@ def rulebook_sparse(index_in: OccupancyIndex, ksize, stride, padding, tag):
     dev = index_in.buf.device
     nbr_fwd = torch.empty((kvol, n_out), dtype=torch.int32, device=dev)
     nbr_bwd = torch.empty((kvol, n_in), dtype=torch.int32, device=dev)
-    _C.check(_C.lib().toda_rulebook_sparse(_p(index_in.buf), *index_in.shape, _p(index_out.buf), *out_shape, index_in.batch,
-                                           _p(index_in.coords), n_in, _p(out_coords), n_out, _C.ints(ksize),
-                                           _C.ints(stride), _C.ints(padding), _p(nbr_fwd), _p(nbr_bwd), _stream()),
-             "toda_rulebook_sparse")
+    with _timed("rulebook_sparse", n_in=n_in, n_out=n_out, kvol=kvol):
+        _C.check(_C.lib().toda_rulebook_sparse(_p(index_in.buf), *index_in.shape, _p(index_out.buf), *out_shape,
+                                               index_in.batch, _p(index_in.coords), n_in, _p(out_coords), n_out,
+                                               _C.ints(ksize), _C.ints(stride), _C.ints(padding), _p(nbr_fwd), _p(nbr_bwd),
+                                               _stream()), "toda_rulebook_sparse")
     _count(2)
     rb = Rulebook(False, list(ksize), list(stride), list(padding), index_in.shape, out_shape, n_in, n_out, out_coords,
                   nbr_fwd, nbr_bwd)
@@ -324,10 +364,14 @@ def _repack(weight, transpose, mirror):
     return out
 
 
-def _conv_call(x, cin, nbr, n_out, kvol, w, cout, bias, precision):
+def _conv_call(x, cin, nbr, n_out, kvol, w, cout, bias, precision, what="conv_fwd", rb=None):
     y = torch.empty((n_out, cout), dtype=torch.float32, device=x.device)
-    _C.check(_C.lib().toda_spconv_fwd(_p(x), x.shape[0], cin, _p(nbr), n_out, kvol, _p(w), cout, _p(bias), _p(y),
-                                      precision, _stream()), "toda_spconv_fwd")
+    L = _C.lib()
+    ws_bytes = L.toda_spconv_fwd_workspace_bytes(x.shape[0], cin, cout, kvol, precision)
+    ws = _workspace("conv", ws_bytes, x.device) if ws_bytes else None
+    with _timed(what, n_in=x.shape[0], n_out=n_out, cin=cin, cout=cout, kvol=kvol, precision=precision, rb=id(rb)):
+        _C.check(L.toda_spconv_fwd(_p(x), x.shape[0], cin, _p(nbr), n_out, kvol, _p(w), cout, _p(bias), _p(y), precision,
+                                   _p(ws), ws.numel() if ws is not None else 0, _stream()), "toda_spconv_fwd")
     _count(1)
     return y
 
@@ -341,7 +385,7 @@ class _SparseConv(torch.autograd.Function):
         assert x.shape == (rb.n_in, cin), (x.shape, rb.n_in, cin)
         w = _repack(weight, False, False)
         b = bias.contiguous() if bias is not None else None
-        y = _conv_call(x, cin, rb.nbr_fwd, rb.n_out, rb.kvol, w, cout, b, precision)
+        y = _conv_call(x, cin, rb.nbr_fwd, rb.n_out, rb.kvol, w, cout, b, precision, "conv_fwd", rb)
         ctx.save_for_backward(x, weight)
         ctx.rb, ctx.precision, ctx.has_bias = rb, precision, bias is not None
         return y
@@ -358,13 +402,15 @@ class _SparseConv(torch.autograd.Function):
             # dgrad = the same gather-GEMM on the input-stationary table with transposed weights
             wt = _repack(weight, True, rb.subm)
             table = rb.nbr_fwd if rb.subm else rb.nbr_bwd
-            dx = _conv_call(dy, cout, table, rb.n_in, rb.kvol, wt, cin, None, precision)
+            dx = _conv_call(dy, cout, table, rb.n_in, rb.kvol, wt, cin, None, precision, "conv_dgrad", rb)
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(weight)
-            ws_bytes = L.toda_spconv_wgrad_workspace_bytes(rb.n_out, rb.kvol, cin, cout)
+            ws_bytes = L.toda_spconv_wgrad_workspace_bytes(rb.n_in, rb.n_out, rb.kvol, cin, cout, precision)
             ws = _workspace("wgrad", ws_bytes, dy.device)
-            _C.check(L.toda_spconv_wgrad(_p(x), rb.n_in, cin, _p(rb.nbr_fwd), rb.n_out, rb.kvol, _p(dy), cout, _p(dw), _p(ws),
-                                         ws.numel(), precision, _stream()), "toda_spconv_wgrad")
+            with _timed("conv_wgrad", n_in=rb.n_in, n_out=rb.n_out, cin=cin, cout=cout, kvol=rb.kvol, precision=precision,
+                        rb=id(rb)):
+                _C.check(L.toda_spconv_wgrad(_p(x), rb.n_in, cin, _p(rb.nbr_fwd), rb.n_out, rb.kvol, _p(dy), cout, _p(dw),
+                                             _p(ws), ws.numel(), precision, _stream()), "toda_spconv_wgrad")
             _count(2)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = col_sum(dy)
@@ -401,9 +447,10 @@ class _BNAct(torch.autograd.Function):
         if training:
             mean = torch.empty_like(scale)
             rstd = torch.empty_like(scale)
-            _C.check(L.toda_bn_stats(_p(y), n, c, _p(gamma), _p(beta), float(eps), float(momentum), _p(running_mean),
-                                     _p(running_var), _p(scale), _p(shift), _p(mean), _p(rstd), _p(ws), ws.numel(),
-                                     _stream()), "toda_bn_stats")
+            with _timed("bn_stats", n=n, c=c):
+                _C.check(L.toda_bn_stats(_p(y), n, c, _p(gamma), _p(beta), float(eps), float(momentum), _p(running_mean),
+                                         _p(running_var), _p(scale), _p(shift), _p(mean), _p(rstd), _p(ws), ws.numel(),
+                                         _stream()), "toda_bn_stats")
             _count(2)
         else:
             _C.check(L.toda_bn_eval_coeffs(_p(gamma), _p(beta), _p(running_mean), _p(running_var), float(eps), c, _p(scale),
@@ -413,7 +460,8 @@ class _BNAct(torch.autograd.Function):
             rstd = torch.rsqrt(running_var + eps) if y.requires_grad or gamma.requires_grad else None
         res = residual.contiguous() if residual is not None else None
         a = torch.empty_like(y)
-        _C.check(L.toda_bn_apply(_p(y), n, c, _p(scale), _p(shift), _p(res), int(relu), _p(a), _stream()), "toda_bn_apply")
+        with _timed("bn_apply", n=n, c=c, residual=res is not None):
+            _C.check(L.toda_bn_apply(_p(y), n, c, _p(scale), _p(shift), _p(res), int(relu), _p(a), _stream()), "toda_bn_apply")
         _count(1)
         ctx.save_for_backward(y, a, gamma, mean, rstd)
         ctx.cfg = (bool(training), bool(relu), residual is not None)
@@ -431,8 +479,9 @@ class _BNAct(torch.autograd.Function):
         dgamma = torch.empty((c,), dtype=torch.float32, device=y.device)
         dbeta = torch.empty_like(dgamma)
         ws = _workspace("bn", L.toda_bn_workspace_bytes(c), y.device)
-        _C.check(L.toda_bn_bwd(_p(da), _p(a), _p(y), n, c, _p(gamma), _p(mean), _p(rstd), int(relu), int(training), _p(dy),
-                               _p(dres), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _stream()), "toda_bn_bwd")
+        with _timed("bn_bwd", n=n, c=c, residual=has_res):
+            _C.check(L.toda_bn_bwd(_p(da), _p(a), _p(y), n, c, _p(gamma), _p(mean), _p(rstd), int(relu), int(training),
+                                   _p(dy), _p(dres), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _stream()), "toda_bn_bwd")
         _count(3)
         return dy, dgamma, dbeta, None, None, None, None, None, dres, None
 
@@ -457,8 +506,9 @@ class _BEVScatter(torch.autograd.Function):
         coords = _need(coords, torch.int32, "indices")
         n, c = features.shape
         out = torch.empty((batch, c * d, h, w), dtype=torch.float32, device=features.device)
-        _C.check(_C.lib().toda_bev_scatter_fwd(_p(features), _p(coords), n, c, batch, d, h, w, _p(out), _stream()),
-                 "toda_bev_scatter_fwd")
+        with _timed("bev_scatter_fwd", n=n, c=c, out_elems=out.numel()):
+            _C.check(_C.lib().toda_bev_scatter_fwd(_p(features), _p(coords), n, c, batch, d, h, w, _p(out), _stream()),
+                     "toda_bev_scatter_fwd")
         _count(2)
         ctx.save_for_backward(coords)
         ctx.dims = (n, c, batch, d, h, w)
@@ -470,8 +520,9 @@ class _BEVScatter(torch.autograd.Function):
         n, c, batch, d, h, w = ctx.dims
         dout = dout.contiguous()
         df = torch.empty((n, c), dtype=torch.float32, device=dout.device)
-        _C.check(_C.lib().toda_bev_scatter_bwd(_p(dout), _p(coords), n, c, batch, d, h, w, _p(df), _stream()),
-                 "toda_bev_scatter_bwd")
+        with _timed("bev_scatter_bwd", n=n, c=c):
+            _C.check(_C.lib().toda_bev_scatter_bwd(_p(dout), _p(coords), n, c, batch, d, h, w, _p(df), _stream()),
+                     "toda_bev_scatter_bwd")
         _count(1)
         return df, None, None, None, None, None
 

@@ -50,10 +50,12 @@ class MeanVFE(nn.Module):
     def voxelize(self, batch_dict):
         points = batch_dict["points"]                       # (N, 1+F): [b, x, y, z, ...]
         batch_size = int(batch_dict["batch_size"])
-        bidx = points[:, 0].contiguous()
-        # frames are stored back to back by collate_batch (dataset.py L173-178)
-        bounds = torch.arange(batch_size + 1, device=points.device, dtype=torch.float32)
-        offsets = torch.searchsorted(bidx, bounds).int()
+        offsets = batch_dict.get("point_frame_offsets")
+        if offsets is None:
+            # frames are stored back to back by collate_batch (dataset.py L173-178)
+            bidx = points[:, 0].contiguous()
+            bounds = torch.arange(batch_size + 1, device=points.device, dtype=torch.float32)
+            offsets = torch.searchsorted(bidx, bounds).int()
         mode = "train" if self.training else "test"
         max_voxels = self._cfg("MAX_NUMBER_OF_VOXELS")
         max_voxels = max_voxels[mode] if hasattr(max_voxels, "__getitem__") and not isinstance(max_voxels, int) else max_voxels
