@@ -8,36 +8,95 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kPartials = 2 * kNumSMs;  // CTAs in the reduction grids
 
-// partial sums of up to two quantities per channel.  C <= 256; thread layout: tx = channel lane, ty = row lane.
+// per-CTA partial sums of up to two quantities per channel; C % 4 == 0 path: one thread owns 4 channels (float4
+// loads) and walks rows with four independent loads in flight per array.
 // mode 0: (y, y*y)      mode 1: (g, g*xhat) with g = da*(a>0)     mode 2: (dy, -)
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) col_reduce_vec_kernel(const float *__restrict__ p0, const float *__restrict__ p1,
+                                                                  const float *__restrict__ p2, int n, int c,
+                                                                  const float *__restrict__ mean, const float *__restrict__ rstd,
+                                                                  int relu, double *__restrict__ partial) {
+    __shared__ double s0[kThreads * 4], s1[kThreads * 4];
+    const int tpr = c >> 2;                       // threads per row
+    const int rpi = kThreads / tpr;               // rows per CTA iteration
+    const int tx = threadIdx.x % tpr, ty = threadIdx.x / tpr;
+    double a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
+    float4 m4 = make_float4(0, 0, 0, 0), r4 = make_float4(0, 0, 0, 0);
+    if (MODE == 1) { m4 = __ldg((const float4 *)mean + tx); r4 = __ldg((const float4 *)rstd + tx); }
+    const long long stride = (long long)gridDim.x * rpi;
+    const bool active = ty < rpi;
+    for (long long r = (long long)blockIdx.x * rpi + ty; active && r < n; r += 4 * stride) {
+        float4 v0[4], v1[4], v2[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            long long rr = r + u * stride;
+            ok[u] = rr < n;
+            size_t e = ok[u] ? (size_t)rr * tpr + tx : 0;
+            v0[u] = __ldg((const float4 *)p0 + e);
+            if (MODE == 1) { v1[u] = __ldg((const float4 *)p1 + e); v2[u] = __ldg((const float4 *)p2 + e); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (!ok[u]) continue;
+            float x[4] = {v0[u].x, v0[u].y, v0[u].z, v0[u].w};
+            if (MODE == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { a0[q] += x[q]; a1[q] += (double)x[q] * x[q]; }
+            } else if (MODE == 1) {
+                float av[4] = {v1[u].x, v1[u].y, v1[u].z, v1[u].w}, yv[4] = {v2[u].x, v2[u].y, v2[u].z, v2[u].w};
+                float mm[4] = {m4.x, m4.y, m4.z, m4.w}, rs[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float g = (relu && !(av[q] > 0.f)) ? 0.f : x[q];
+                    float xh = (yv[q] - mm[q]) * rs[q];
+                    a0[q] += g; a1[q] += (double)g * xh;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) a0[q] += x[q];
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { s0[threadIdx.x * 4 + q] = a0[q]; s1[threadIdx.x * 4 + q] = a1[q]; }
+    __syncthreads();
+    if ((int)threadIdx.x < c) {
+        // channel ch = threadIdx.x lives in thread tx = ch/4, slot ch%4 of every row lane ty
+        int ch = threadIdx.x, txx = ch >> 2, q = ch & 3;
+        double t0 = 0.0, t1 = 0.0;
+        for (int j = 0; j < rpi; ++j) { t0 += s0[(j * tpr + txx) * 4 + q]; t1 += s1[(j * tpr + txx) * 4 + q]; }
+        partial[((size_t)blockIdx.x * 2 + 0) * c + ch] = t0;
+        partial[((size_t)blockIdx.x * 2 + 1) * c + ch] = t1;
+    }
+}
+
+// scalar fallback for channel counts that are not a multiple of 4 (e.g. the 5 point features)
 template <int MODE>
 __global__ void __launch_bounds__(kThreads) col_reduce_kernel(const float *__restrict__ p0, const float *__restrict__ p1,
                                                               const float *__restrict__ p2, int n, int c,
                                                               const float *__restrict__ mean, const float *__restrict__ rstd,
                                                               int relu, double *__restrict__ partial) {
-    // CTA handles rows blockIdx.x, blockIdx.x+grid, ... in chunks; threads stride over (row, channel) pairs
     __shared__ double s0[kThreads], s1[kThreads];
     const int cpad = c <= 16 ? 16 : (c <= 32 ? 32 : (c <= 64 ? 64 : (c <= 128 ? 128 : 256)));
-    const int rows_per_iter = kThreads / (cpad < kThreads ? cpad : kThreads);
+    const int rows_per_iter = kThreads / cpad;
     const int tx = threadIdx.x % cpad, ty = threadIdx.x / cpad;
     double a0 = 0.0, a1 = 0.0;
-    if (cpad <= kThreads) {
-        float m = 0.f, rs = 0.f;
-        if (MODE == 1 && tx < c) { m = mean[tx]; rs = rstd[tx]; }
-        for (long long r = (long long)blockIdx.x * rows_per_iter + ty; r < n; r += (long long)gridDim.x * rows_per_iter) {
-            if (tx < c) {
-                size_t e = (size_t)r * c + tx;
-                if (MODE == 0) {
-                    float v = __ldg(p0 + e);
-                    a0 += v; a1 += (double)v * v;
-                } else if (MODE == 1) {
-                    float g = __ldg(p0 + e);
-                    if (relu && !(__ldg(p1 + e) > 0.f)) g = 0.f;
-                    float xh = (__ldg(p2 + e) - m) * rs;
-                    a0 += g; a1 += (double)g * xh;
-                } else {
-                    a0 += __ldg(p0 + e);
-                }
+    float m = 0.f, rs = 0.f;
+    if (MODE == 1 && tx < c) { m = mean[tx]; rs = rstd[tx]; }
+    for (long long r = (long long)blockIdx.x * rows_per_iter + ty; r < n; r += (long long)gridDim.x * rows_per_iter) {
+        if (tx < c) {
+            size_t e = (size_t)r * c + tx;
+            if (MODE == 0) {
+                float v = __ldg(p0 + e);
+                a0 += v; a1 += (double)v * v;
+            } else if (MODE == 1) {
+                float g = __ldg(p0 + e);
+                if (relu && !(__ldg(p1 + e) > 0.f)) g = 0.f;
+                float xh = (__ldg(p2 + e) - m) * rs;
+                a0 += g; a1 += (double)g * xh;
+            } else {
+                a0 += __ldg(p0 + e);
             }
         }
     }
@@ -51,14 +110,35 @@ __global__ void __launch_bounds__(kThreads) col_reduce_kernel(const float *__res
     }
 }
 
+template <int MODE>
+static void launch_col_reduce(const float *p0, const float *p1, const float *p2, int n, int c, const float *mean,
+                              const float *rstd, int relu, double *partial, cudaStream_t st) {
+    if (c % 4 == 0 && kThreads % (c / 4) == 0)
+        col_reduce_vec_kernel<MODE><<<kPartials, kThreads, 0, st>>>(p0, p1, p2, n, c, mean, rstd, relu, partial);
+    else
+        col_reduce_kernel<MODE><<<kPartials, kThreads, 0, st>>>(p0, p1, p2, n, c, mean, rstd, relu, partial);
+}
+
+// fixed-order sum of the per-CTA partials of one channel: one warp per channel, lanes stride over the partials
+__device__ __forceinline__ void warp_sum_partials(const double *__restrict__ partial, int nblocks, int c, int ch, double &s,
+                                                  double &ss) {
+    const int lane = threadIdx.x & 31;
+    double a = 0.0, b = 0.0;
+    for (int j = lane; j < nblocks; j += 32) { a += partial[((size_t)j * 2) * c + ch]; b += partial[((size_t)j * 2 + 1) * c + ch]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    s = a; ss = b;
+}
+
 __global__ void bn_finalize_kernel(const double *__restrict__ partial, int nblocks, int n, int c,
                                    const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float momentum,
                                    float *running_mean, float *running_var, float *scale, float *shift, float *save_mean,
                                    float *save_rstd) {
-    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (ch >= c) return;
-    double s = 0.0, ss = 0.0;
-    for (int b = 0; b < nblocks; ++b) { s += partial[((size_t)b * 2) * c + ch]; ss += partial[((size_t)b * 2 + 1) * c + ch]; }
+    double s, ss;
+    warp_sum_partials(partial, nblocks, c, ch, s, ss);
+    if ((threadIdx.x & 31) != 0) return;
     double mean = n > 0 ? s / n : 0.0;
     double var = n > 0 ? ss / n - mean * mean : 0.0;
     if (var < 0.0) var = 0.0;
@@ -117,10 +197,11 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const float *__restr
 
 __global__ void bn_bwd_finalize_kernel(const double *__restrict__ partial, int nblocks, int c, float *dgamma, float *dbeta,
                                        float *sums /* [2c]: sum_g, sum_g_xhat */) {
-    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (ch >= c) return;
-    double s = 0.0, sx = 0.0;
-    for (int b = 0; b < nblocks; ++b) { s += partial[((size_t)b * 2) * c + ch]; sx += partial[((size_t)b * 2 + 1) * c + ch]; }
+    double s, sx;
+    warp_sum_partials(partial, nblocks, c, ch, s, sx);
+    if ((threadIdx.x & 31) != 0) return;
     if (dbeta) dbeta[ch] = (float)s;
     if (dgamma) dgamma[ch] = (float)sx;
     sums[ch] = (float)s;
@@ -154,11 +235,11 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float *__r
 }
 
 __global__ void col_sum_finalize_kernel(const double *__restrict__ partial, int nblocks, int c, float *out) {
-    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (ch >= c) return;
-    double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += partial[((size_t)b * 2) * c + ch];
-    out[ch] = (float)s;
+    double s, unused;
+    warp_sum_partials(partial, nblocks, c, ch, s, unused);
+    if ((threadIdx.x & 31) == 0) out[ch] = (float)s;
 }
 
 size_t bn_ws_bytes(int c) { return align_up((size_t)kPartials * 2 * c * sizeof(double) + 2 * c * sizeof(float), 256); }
@@ -175,9 +256,9 @@ extern "C" int toda_bn_stats(const float *y, int n, int c, const float *gamma, c
     if (workspace_bytes < bn_ws_bytes(c)) { toda_set_error("bn_stats: workspace too small"); return TODA_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
     double *partial = (double *)workspace;
-    col_reduce_kernel<0><<<kPartials, kThreads, 0, st>>>(y, nullptr, nullptr, n, c, nullptr, nullptr, 0, partial);
+    launch_col_reduce<0>(y, nullptr, nullptr, n, c, nullptr, nullptr, 0, partial, st);
     TODA_LAUNCH_OK();
-    bn_finalize_kernel<<<ceil_div(c, 128), 128, 0, st>>>(partial, kPartials, n, c, gamma, beta, eps, momentum, running_mean,
+    bn_finalize_kernel<<<ceil_div(c * 32, 128), 128, 0, st>>>(partial, kPartials, n, c, gamma, beta, eps, momentum, running_mean,
                                                         running_var, scale, shift, save_mean, save_rstd);
     TODA_LAUNCH_OK();
     return TODA_OK;
@@ -217,9 +298,9 @@ extern "C" int toda_bn_bwd(const float *da, const float *a, const float *y, int 
     cudaStream_t st = (cudaStream_t)stream;
     double *partial = (double *)workspace;
     float *sums = (float *)((char *)workspace + (size_t)kPartials * 2 * c * sizeof(double));
-    col_reduce_kernel<1><<<kPartials, kThreads, 0, st>>>(da, a, y, n, c, save_mean, save_rstd, relu, partial);
+    launch_col_reduce<1>(da, a, y, n, c, save_mean, save_rstd, relu, partial, st);
     TODA_LAUNCH_OK();
-    bn_bwd_finalize_kernel<<<ceil_div(c, 128), 128, 0, st>>>(partial, kPartials, c, dgamma, dbeta, sums);
+    bn_bwd_finalize_kernel<<<ceil_div(c * 32, 128), 128, 0, st>>>(partial, kPartials, c, dgamma, dbeta, sums);
     TODA_LAUNCH_OK();
     if (n > 0) {
         long long total = (long long)n * c;
@@ -235,9 +316,9 @@ extern "C" int toda_col_sum(const float *dy, int n, int c, float *out, void *wor
     if (workspace_bytes < bn_ws_bytes(c)) { toda_set_error("col_sum: workspace too small"); return TODA_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
     double *partial = (double *)workspace;
-    col_reduce_kernel<2><<<kPartials, kThreads, 0, st>>>(dy, nullptr, nullptr, n, c, nullptr, nullptr, 0, partial);
+    launch_col_reduce<2>(dy, nullptr, nullptr, n, c, nullptr, nullptr, 0, partial, st);
     TODA_LAUNCH_OK();
-    col_sum_finalize_kernel<<<ceil_div(c, 128), 128, 0, st>>>(partial, kPartials, c, out);
+    col_sum_finalize_kernel<<<ceil_div(c * 32, 128), 128, 0, st>>>(partial, kPartials, c, out);
     TODA_LAUNCH_OK();
     return TODA_OK;
 }

@@ -10,7 +10,7 @@ int conv_tc_fwd(const float *x, int n_in, int cin, const int32_t *nbr, int n_out
 size_t conv_tc_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol);
 int conv_tc_wgrad(const float *x, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *dy, int cout,
                   float *dw_param, void *workspace, size_t workspace_bytes, cudaStream_t st);
-bool conv_tc_supported(int cin, int cout);
+bool conv_tc_supported(int cin, int cout, int kvol);
 bool conv_tc_wgrad_supported(int cin, int cout);
 size_t conv_tc_wgrad_workspace_bytes(int n_in, int n_out, int kvol, int cin, int cout);
 
@@ -179,19 +179,27 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_f32_kernel(const float *_
 }
 
 // fixed-order reduction over splits, written in the parameter layout (Cout, kvol, Cin)
+// fixed-order reduction over splits, written in the parameter layout (Cout, kvol, Cin)
 __global__ void wgrad_reduce_kernel(const float *__restrict__ partial, int splits, int kvol, int cin, int cout,
                                     float *__restrict__ dw_param) {
     size_t per = (size_t)kvol * cin * cout;
-    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < per; e += (size_t)gridDim.x * blockDim.x) {
-        // e indexes the parameter layout: (co, k, ci)
-        int ci = (int)(e % cin);
-        size_t t = e / cin;
-        int k = (int)(t % kvol);
-        int co = (int)(t / kvol);
-        size_t src = ((size_t)k * cin + ci) * cout + co;
+    const int sub = threadIdx.x & 7;   // 8 lanes per element walk the splits; fixed shuffle tree => deterministic
+    for (size_t e = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 3; e < ((per + 31) & ~(size_t)31);
+         e += ((size_t)gridDim.x * blockDim.x) >> 3) {
         float s = 0.f;
-        for (int sp = 0; sp < splits; ++sp) s += partial[sp * per + src];
-        dw_param[e] = s;
+        if (e < per) {
+            // e indexes the parameter layout: (co, k, ci)
+            int ci = (int)(e % cin);
+            size_t t = e / cin;
+            int k = (int)(t % kvol);
+            int co = (int)(t / kvol);
+            size_t src = ((size_t)k * cin + ci) * cout + co;
+            for (int sp = sub; sp < splits; sp += 8) s += partial[sp * per + src];
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (e < per && sub == 0) dw_param[e] = s;
     }
 }
 
@@ -240,7 +248,7 @@ extern "C" int toda_weight_repack(const float *w_param, int kvol, int cin, int c
 }
 
 extern "C" size_t toda_spconv_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol, int precision) {
-    if (precision == TODA_CONV_BF16 && n_in >= 0 && cin > 0 && cout > 0 && kvol > 0)
+    if (precision == TODA_CONV_BF16 && n_in >= 0 && cin > 0 && cout > 0 && kvol > 0 && conv_tc_supported(cin, cout, kvol))
         return conv_tc_fwd_workspace_bytes(n_in, cin, cout, kvol);
     return 0;
 }
@@ -253,9 +261,9 @@ extern "C" int toda_spconv_fwd(const float *x, int n_in, int cin, const int32_t 
     TODA_CHECK_ARG(x && nbr && w && y, "spconv_fwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     TODA_CHECK_ARG(precision == TODA_CONV_FP32 || precision == TODA_CONV_BF16, "spconv_fwd: unknown precision %d", precision);
-    // kernel selection by shape: the tensor-core kernel needs Cin % 16 == 0 (UMMA K) and Cout in {16,32,64,128};
-    // the 4/5-channel input layer (conv_input) runs on the FFMA kernel in either mode.
-    if (precision == TODA_CONV_BF16 && conv_tc_supported(cin, cout))
+    // kernel selection by shape: the tensor-core kernel covers Cin in {<=16 (zero-padded to 16), 32, 64, 128} and
+    // Cout in {16,32,64,128}; anything else (e.g. the dgrad of the 4/5-channel input layer) runs on the FFMA kernel.
+    if (precision == TODA_CONV_BF16 && conv_tc_supported(cin, cout, kvol))
         return conv_tc_fwd(x, n_in, cin, nbr, n_out, kvol, w, cout, bias, y, workspace, workspace_bytes, st);
     if (cout <= 16) {
         dim3 grid(ceil_div(n_out, 256), ceil_div(cout, 16));
@@ -306,7 +314,7 @@ extern "C" int toda_spconv_wgrad(const float *x, int n_in, int cin, const int32_
     conv_wgrad_f32_kernel<<<grid, kThreads, 0, st>>>(x, cin, nbr, n_out, kvol, dy, cout, rows_per_split, (float *)workspace);
     TODA_LAUNCH_OK();
     size_t per = (size_t)kvol * cin * cout;
-    wgrad_reduce_kernel<<<wave_grid(per, 256), 256, 0, st>>>((const float *)workspace, splits, kvol, cin, cout, dw_param);
+    wgrad_reduce_kernel<<<wave_grid(per * 8, 256), 256, 0, st>>>((const float *)workspace, splits, kvol, cin, cout, dw_param);
     TODA_LAUNCH_OK();
     return TODA_OK;
 }

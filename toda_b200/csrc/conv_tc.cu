@@ -17,6 +17,7 @@
 // No scatter and no atomics: every output row is written once.  dgrad is the same kernel on the
 // input-stationary table with transposed weights.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -30,7 +31,8 @@ constexpr int kThreadsTC = kProducers + 32;
 constexpr int kABytes = kTileM * kChunkK * 2;     // 16 KB
 constexpr int kBBytesMax = 128 * kChunkK * 2;     // 16 KB (Cout <= 128)
 constexpr int kStageBytes = kABytes + kBBytesMax;
-constexpr int kSmemTC = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int kMaxKvol = 27;
+constexpr int kIdxBytes = kMaxKvol * kTileM * 4;  // this tile's slice of the neighbour table (13.5 KB)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -53,6 +55,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void st_shared_zero16(uint32_t dst) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
 }
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
@@ -91,35 +96,74 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
 // byte offset of 16-byte piece `p` of row `r` inside a [rows][64 bf16] SWIZZLE_128B tile
 __device__ __forceinline__ uint32_t sw128_offset(int r, int p) { return (uint32_t)(r * 128 + ((p ^ (r & 7)) << 4)); }
 
-template <int COUT>
-__global__ void __launch_bounds__(kThreadsTC, 1) conv_tc_fwd_kernel(const __nv_bfloat16 *__restrict__ xb, int cin,
-                                                                    const int *__restrict__ nbr, int n_out, int kvol,
-                                                                    const __nv_bfloat16 *__restrict__ wb /*[COUT][kvol*cin]*/,
-                                                                    const float *__restrict__ bias, float *__restrict__ y) {
-    static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 128, "UMMA N");
-    constexpr int kTmemCols = COUT < 32 ? 32 : COUT;   // power of two >= 32
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
-    const uint32_t bar_base = base + kStages * kStageBytes;
-    const uint32_t full_bar = bar_base, empty_bar = bar_base + 8 * kStages, accum_bar = bar_base + 16 * kStages;
-    const uint32_t tmem_slot = bar_base + 16 * kStages + 8;
-    volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+// ---- forward / dgrad kernel: persistent, warp-specialised --------------------------------------------------
+//   warps 0-7   producers : gather A + copy B for every K chunk into the stage ring (cp.async, SWIZZLE_128B)
+//   warp  8     MMA       : one thread issues tcgen05.mma; accumulators double-buffered in TMEM
+//   warps 9-12  epilogue  : tcgen05.ld -> + bias -> fp32 rows to global, overlapped with the next tile's MMAs
+//   warp  13    indexer   : streams the next tile's slice of the neighbour table into shared memory
+// A CTA stays resident (grid = #SMs) and walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...
+// The producer loop is the critical path (ncu: it is issue-bound, not memory-bound), so everything in it is a
+// compile-time constant or hoisted: CIN is a template parameter (no divisions), swizzled shared-memory offsets
+// are per-thread constants, and the table slice is read from shared memory.
+constexpr int kProdThreads = 256;
+constexpr int kFwdThreads = kProdThreads + 32 + 128 + 32;   // 448
+constexpr int kFwdSmemBudget = 200 * 1024;
+template <int COUT> struct FwdCfg {
+    static constexpr int kBBytes = COUT * kChunkK * 2;
+    static constexpr int kStage = kABytes + kBBytes;
+    static constexpr int kStagesRaw = (kFwdSmemBudget - 2 * kIdxBytes) / kStage;
+    static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+    static constexpr int kSmem = kStages * kStage + 1024 + 256 + 2 * kIdxBytes;
+    static constexpr int kTmemCols = 2 * COUT < 32 ? 32 : 2 * COUT;
+};
 
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int row0 = blockIdx.x * kTileM;
-    const int ktot = kvol * cin;
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_bfloat16 *__restrict__ xb,
+                                                                     const int *__restrict__ nbr, int n_out, int kvol,
+                                                                     const __nv_bfloat16 *__restrict__ wb /*[COUT][kvol*CIN]*/,
+                                                                     const float *__restrict__ bias, float *__restrict__ y,
+                                                                     int num_tiles) {
+    static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 128, "UMMA N");
+    static_assert(CIN == 16 || CIN == 32 || CIN == 64 || CIN == 128, "row = 32..256 bytes of bf16");
+    using C = FwdCfg<COUT>;
+    constexpr int S = C::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t bar_base = base + S * C::kStage;
+    const uint32_t full_bar = bar_base, empty_bar = bar_base + 8 * S;
+    const uint32_t acc_full = bar_base + 16 * S, acc_empty = acc_full + 16;
+    const uint32_t idx_full = acc_full + 32, idx_empty = acc_full + 48;
+    const uint32_t tmem_slot = acc_full + 64;
+    const uint32_t idx_base = bar_base + 256;
+    volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *)(smem_raw + (tmem_slot - raw));
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ktot = kvol * CIN;
     const int nchunks = (ktot + kChunkK - 1) / kChunkK;
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(full_bar + 8 * s, kProducers);
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_bar + 8 * s, 2 * kProdThreads);   // cp.async completions + releasing arrivals
             mbar_init(empty_bar + 8 * s, 1);
         }
-        mbar_init(accum_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(acc_full + 8 * b, 1);
+            mbar_init(acc_empty + 8 * b, 128);
+            mbar_init(idx_full + 8 * b, 64);
+            mbar_init(idx_empty + 8 * b, kProdThreads);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols) : "memory");
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(C::kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -127,92 +171,141 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv_tc_fwd_kernel(const __nv_b
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    if (warp < 4) {
-        // ------------------------------------------------------------------ producers
+    if (warp < 8) {
+        // ------------------------------------------------------------------ producers (256 threads)
         const int p = tid & 7;          // 16-byte piece of the 128-byte chunk row
-        const int rbase = tid >> 3;     // rows rbase + 16*i
-        for (int c = 0; c < nchunks; ++c) {
-            const int s = c % kStages, use = c / kStages;
-            if (use > 0) mbar_wait(empty_bar + 8 * s, (use - 1) & 1);
-            const uint32_t a_tile = base + s * kStageBytes, b_tile = a_tile + kABytes;
-            const int kk = c * kChunkK + p * 8;          // position of this thread's piece on the flattened K axis
-            const bool k_ok = kk < ktot;
-            const int k = k_ok ? kk / cin : 0, ci = k_ok ? kk % cin : 0;
-            int src[8];
+        const int rbase = tid >> 3;     // rows rbase + 32*i, i = 0..3  (all share r & 7 == rbase & 7)
+        const uint32_t piece_off = (uint32_t)(rbase * 128 + ((p ^ (rbase & 7)) << 4));   // + i * 4096 per row step
+        // which kernel offset / channel this thread's piece belongs to, per chunk c:
+        //   CIN=16: k = 4c + p/2, ci = (p&1)*8      CIN=32: k = 2c + p/4, ci = (p&3)*8
+        //   CIN=64: k = c,        ci = p*8          CIN=128: k = c/2,     ci = (c&1)*64 + p*8
+        constexpr int kOffsPerChunk = CIN >= 64 ? 1 : 64 / CIN;
+        const int k_sub = CIN >= 64 ? 0 : p / (CIN / 8);
+        const int ci_lo = CIN >= 64 ? p * 8 : (p % (CIN / 8)) * 8;
+        const char *xbytes = (const char *)xb + ci_lo * 2;
+        const char *wbytes = (const char *)wb + (size_t)rbase * ktot * 2 + p * 16;
+        const uint32_t idx_lane = idx_base + 4 * rbase;
+        int g = 0, it = 0;              // global chunk counter (stage ring position), tile counter
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const int ib = it & 1;
+            mbar_wait(idx_full + 8 * ib, (it >> 1) & 1);
+            const uint32_t idx_tile = idx_lane + ib * kIdxBytes;
+            for (int c = 0; c < nchunks; ++c, ++g) {
+                const int s = g % S, use = g / S;
+                if (use > 0) mbar_wait(empty_bar + 8 * s, (use - 1) & 1);
+                const uint32_t a_dst = base + s * C::kStage + piece_off, b_dst = a_dst + kABytes;
+                const int k = CIN == 128 ? (c >> 1) : c * kOffsPerChunk + k_sub;
+                const bool k_ok = k < kvol;      // only the K tail of CIN=16/32 layers can miss
+                const int ci_hi = CIN == 128 ? (c & 1) * 64 : 0;
+                int src[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                int r = row0 + rbase + 16 * i;
-                src[i] = (k_ok && r < n_out) ? __ldg(nbr + (size_t)k * n_out + r) : -1;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = rbase + 16 * i;
-                const bool ok = src[i] >= 0;
-                const __nv_bfloat16 *g = ok ? xb + (size_t)src[i] * cin + ci : xb;
-                cp_async_16(a_tile + sw128_offset(r, p), g, ok ? 16u : 0u);
-            }
-#pragma unroll
-            for (int j = 0; j < COUT / 16; ++j) {
-                const int r = rbase + 16 * j;
-                const __nv_bfloat16 *g = k_ok ? wb + (size_t)r * ktot + kk : wb;
-                cp_async_16(b_tile + sw128_offset(r, p), g, k_ok ? 16u : 0u);
-            }
-            cp_async_arrive_noinc(full_bar + 8 * s);
-        }
-        // ------------------------------------------------------------------ epilogue (same four warps)
-        mbar_wait(accum_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = row0 + warp * 32 + (tid & 31);       // TMEM lane = tile row; warp w owns lanes 32w..32w+31
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-#pragma unroll
-        for (int n0 = 0; n0 < COUT; n0 += 16) {
-            uint32_t v[16];
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                  "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                : "r"(taddr + n0));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < n_out) {
-                float4 *dst = (float4 *)(y + (size_t)row * COUT + n0);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float4 o;
-                    o.x = __uint_as_float(v[4 * q + 0]) + (bias ? __ldg(bias + n0 + 4 * q + 0) : 0.f);
-                    o.y = __uint_as_float(v[4 * q + 1]) + (bias ? __ldg(bias + n0 + 4 * q + 1) : 0.f);
-                    o.z = __uint_as_float(v[4 * q + 2]) + (bias ? __ldg(bias + n0 + 4 * q + 2) : 0.f);
-                    o.w = __uint_as_float(v[4 * q + 3]) + (bias ? __ldg(bias + n0 + 4 * q + 3) : 0.f);
-                    dst[q] = o;
+                for (int i = 0; i < 4; ++i) {
+                    src[i] = -1;
+                    if (k_ok) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(src[i]) : "r"(idx_tile + 4 * (k * kTileM + 32 * i)));
                 }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    // missing neighbour: plain zero store (a zero-size cp.async would still send a request per piece)
+                    if (src[i] >= 0) cp_async_16(a_dst + i * 4096, xbytes + ((size_t)(unsigned)src[i] * CIN + ci_hi) * 2, 16u);
+                    else st_shared_zero16(a_dst + i * 4096);
+                }
+#pragma unroll
+                for (int j = 0; j < (COUT + 31) / 32; ++j) {
+                    if (rbase + 32 * j < COUT) {
+                        if (k_ok) cp_async_16(b_dst + j * 4096, wbytes + ((size_t)j * 32 * ktot + (size_t)c * kChunkK) * 2, 16u);
+                        else st_shared_zero16(b_dst + j * 4096);
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // zero stores are generic-proxy writes
+                cp_async_arrive_noinc(full_bar + 8 * s);
+                mbar_arrive(full_bar + 8 * s);
             }
+            mbar_arrive(idx_empty + 8 * ib);   // this tile's table slice has been consumed
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    } else {
-        // ------------------------------------------------------------------ MMA issuer (one thread of warp 4)
-        if ((tid & 31) == 0) {
+    } else if (warp == 8) {
+        // ------------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(kTileM, COUT);
-            for (int c = 0; c < nchunks; ++c) {
-                const int s = c % kStages, use = c / kStages;
-                mbar_wait(full_bar + 8 * s, use & 1);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async writes -> async-proxy reads
+            int g = 0, it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+                const int ab = it & 1, ause = it >> 1;
+                if (ause > 0) mbar_wait(acc_empty + 8 * ab, (ause - 1) & 1);   // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_tile = base + s * kStageBytes, b_tile = a_tile + kABytes;
-                const int ksteps = min(kChunkK, ktot - c * kChunkK) / 16;     // UMMA K = 16 bf16 = 32 bytes
-                for (int j = 0; j < ksteps; ++j) {
-                    uint64_t ad = make_desc_k_sw128(a_tile + j * 32);
-                    uint64_t bd = make_desc_k_sw128(b_tile + j * 32);
-                    umma_bf16(tmem_base, ad, bd, idesc, (c | j) != 0);
+                const uint32_t d_tmem = tmem_base + ab * COUT;
+                for (int c = 0; c < nchunks; ++c, ++g) {
+                    const int s = g % S, use = g / S;
+                    mbar_wait(full_bar + 8 * s, use & 1);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_tile = base + s * C::kStage, b_tile = a_tile + kABytes;
+                    const int ksteps = min(kChunkK, ktot - c * kChunkK) / 16;     // UMMA K = 16 bf16 = 32 bytes
+                    for (int j = 0; j < ksteps; ++j) {
+                        uint64_t ad = make_desc_k_sw128(a_tile + j * 32);
+                        uint64_t bd = make_desc_k_sw128(b_tile + j * 32);
+                        umma_bf16(d_tmem, ad, bd, idesc, (c | j) != 0);
+                    }
+                    umma_commit(empty_bar + 8 * s);        // stage reusable once these MMAs have read it
                 }
-                umma_commit(empty_bar + 8 * s);        // stage reusable once these MMAs have read it
+                umma_commit(acc_full + 8 * ab);            // accumulator of this tile complete
             }
-            umma_commit(accum_bar);                    // accumulator complete
         }
         __syncwarp();
+    } else if (warp < 13) {
+        // ------------------------------------------------------------------ epilogue (warps 9..12)
+        const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const int ab = it & 1;
+            mbar_wait(acc_full + 8 * ab, (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = t * kTileM + q * 32 + lane;          // TMEM lane = tile row
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * COUT;
+#pragma unroll
+            for (int n0 = 0; n0 < COUT; n0 += 16) {
+                uint32_t v[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr + n0));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < n_out) {
+                    float4 *dst = (float4 *)(y + (size_t)row * COUT + n0);
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        float4 o;
+                        o.x = __uint_as_float(v[4 * qq + 0]) + (bias ? __ldg(bias + n0 + 4 * qq + 0) : 0.f);
+                        o.y = __uint_as_float(v[4 * qq + 1]) + (bias ? __ldg(bias + n0 + 4 * qq + 1) : 0.f);
+                        o.z = __uint_as_float(v[4 * qq + 2]) + (bias ? __ldg(bias + n0 + 4 * qq + 2) : 0.f);
+                        o.w = __uint_as_float(v[4 * qq + 3]) + (bias ? __ldg(bias + n0 + 4 * qq + 3) : 0.f);
+                        dst[qq] = o;
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(acc_empty + 8 * ab);
+        }
+    } else {
+        // ------------------------------------------------------------------ indexer (warp 13)
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const int ib = it & 1, use = it >> 1;
+            if (use > 0) mbar_wait(idx_empty + 8 * ib, (use - 1) & 1);
+            const uint32_t dst0 = idx_base + ib * kIdxBytes;
+            const int row0 = t * kTileM;
+            for (int e = lane; e < kvol * kTileM; e += 32) {
+                const int k = e >> 7, r = e & (kTileM - 1);
+                if (row0 + r < n_out) cp_async_4(dst0 + 4 * e, nbr + (size_t)k * n_out + row0 + r);
+                else asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst0 + 4 * e), "r"(-1) : "memory");
+            }
+            cp_async_arrive_noinc(idx_full + 8 * ib);
+            mbar_arrive(idx_full + 8 * ib);
+        }
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::kTmemCols) : "memory");
     }
 }
 
@@ -227,25 +320,41 @@ __global__ void f32_to_bf16_kernel(const float *__restrict__ in, long long n4, _
     }
 }
 
-// w [kvol][cin][cout] fp32  ->  wb [cout][kvol*cin] bf16 (K-major rows for the B operand)
-__global__ void weight_to_kmajor_bf16_kernel(const float *__restrict__ w, int kvol, int cin, int cout,
+// x [n][cin] fp32 -> xb [n][cpad] bf16, channels >= cin zero (the 4/5-channel input layer is padded to UMMA K = 16)
+__global__ void f32_to_bf16_pad_kernel(const float *__restrict__ in, long long n, int cin, int cpad,
+                                       __nv_bfloat16 *__restrict__ out) {
+    long long total = n * cpad;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        long long r = e / cpad;
+        int c = (int)(e - r * cpad);
+        out[e] = __float2bfloat16_rn(c < cin ? __ldg(in + r * cin + c) : 0.f);
+    }
+}
+
+// w [kvol][cin][cout] fp32  ->  wb [cout][kvol*cpad] bf16 (K-major rows for the B operand; padded channels zero)
+__global__ void weight_to_kmajor_bf16_kernel(const float *__restrict__ w, int kvol, int cin, int cpad, int cout,
                                              __nv_bfloat16 *__restrict__ wb) {
-    size_t per = (size_t)kvol * cin * cout;
+    size_t per = (size_t)kvol * cpad * cout;
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < per; e += (size_t)gridDim.x * blockDim.x) {
-        size_t kc = e % ((size_t)kvol * cin);
-        int co = (int)(e / ((size_t)kvol * cin));
-        wb[e] = __float2bfloat16_rn(__ldg(w + kc * cout + co));
+        size_t kc = e % ((size_t)kvol * cpad);
+        int co = (int)(e / ((size_t)kvol * cpad));
+        int k = (int)(kc / cpad), ci = (int)(kc % cpad);
+        wb[e] = __float2bfloat16_rn(ci < cin ? __ldg(w + ((size_t)k * cin + ci) * cout + co) : 0.f);
     }
 }
 
 }  // namespace
 
-bool conv_tc_supported(int cin, int cout) {
-    return cin % 16 == 0 && cin >= 16 && cin <= 128 && (cout == 16 || cout == 32 || cout == 64 || cout == 128);
+static inline int pad16(int c) { return c < 16 ? 16 : c; }
+
+bool conv_tc_supported(int cin, int cout, int kvol) {
+    bool cin_ok = (cin >= 1 && cin < 16) || cin == 16 || cin == 32 || cin == 64 || cin == 128;
+    return cin_ok && kvol <= kMaxKvol && (cout == 16 || cout == 32 || cout == 64 || cout == 128);
 }
 
 size_t conv_tc_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol) {
-    return align_up((size_t)n_in * cin * 2, 256) + align_up((size_t)kvol * cin * cout * 2, 256) + 256;
+    int cp = pad16(cin);
+    return align_up((size_t)n_in * cp * 2 + 16, 256) + align_up((size_t)kvol * cp * cout * 2, 256) + 256;
 }
 
 int conv_tc_fwd(const float *x, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *w, int cout,
@@ -255,28 +364,45 @@ int conv_tc_fwd(const float *x, int n_in, int cin, const int32_t *nbr, int n_out
         toda_set_error("spconv_fwd(bf16): workspace %zu < required %zu bytes", workspace_bytes, need);
         return TODA_ERR_WORKSPACE;
     }
+    const int cp = pad16(cin);
     __nv_bfloat16 *xb = (__nv_bfloat16 *)workspace;
-    __nv_bfloat16 *wb = (__nv_bfloat16 *)((char *)workspace + align_up((size_t)n_in * cin * 2, 256));
-    long long n4 = (long long)n_in * cin / 4;
-    if (n4 > 0) {
-        f32_to_bf16_kernel<<<wave_grid(n4, 256), 256, 0, st>>>(x, n4, xb);
+    __nv_bfloat16 *wb = (__nv_bfloat16 *)((char *)workspace + align_up((size_t)n_in * cp * 2 + 16, 256));
+    if (cp == cin) {
+        long long n4 = (long long)n_in * cin / 4;
+        if (n4 > 0) {
+            f32_to_bf16_kernel<<<wave_grid(n4, 256), 256, 0, st>>>(x, n4, xb);
+            TODA_LAUNCH_OK();
+        }
+    } else if (n_in > 0) {
+        f32_to_bf16_pad_kernel<<<wave_grid((int64_t)n_in * cp, 256), 256, 0, st>>>(x, n_in, cin, cp, xb);
         TODA_LAUNCH_OK();
     }
-    weight_to_kmajor_bf16_kernel<<<wave_grid((int64_t)kvol * cin * cout, 256), 256, 0, st>>>(w, kvol, cin, cout, wb);
+    weight_to_kmajor_bf16_kernel<<<wave_grid((int64_t)kvol * cp * cout, 256), 256, 0, st>>>(w, kvol, cin, cp, cout, wb);
     TODA_LAUNCH_OK();
-    int grid = ceil_div(n_out, kTileM);
-#define LAUNCH_TC(CO)                                                                                              \
-    do {                                                                                                           \
-        TODA_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTC)); \
-        conv_tc_fwd_kernel<CO><<<grid, kThreadsTC, kSmemTC, st>>>(xb, cin, nbr, n_out, kvol, wb, bias, y);          \
+    cin = cp;
+    int num_tiles = ceil_div(n_out, kTileM);
+    int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;   // persistent: one CTA per SM walks the tiles
+#define LAUNCH_TC(CI, CO)                                                                                                    \
+    do {                                                                                                                     \
+        TODA_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_kernel<CI, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<CO>::kSmem)); \
+        conv_tc_fwd_kernel<CI, CO><<<grid, kFwdThreads, FwdCfg<CO>::kSmem, st>>>(xb, nbr, n_out, kvol, wb, bias, y, num_tiles); \
     } while (0)
-    switch (cout) {
-        case 16: LAUNCH_TC(16); break;
-        case 32: LAUNCH_TC(32); break;
-        case 64: LAUNCH_TC(64); break;
-        case 128: LAUNCH_TC(128); break;
-        default: toda_set_error("conv_tc_fwd: unsupported cout %d", cout); return TODA_ERR_UNSUPPORTED;
+#define LAUNCH_TC_CO(CI)                                                                                 \
+    switch (cout) {                                                                                      \
+        case 16: LAUNCH_TC(CI, 16); break;                                                               \
+        case 32: LAUNCH_TC(CI, 32); break;                                                               \
+        case 64: LAUNCH_TC(CI, 64); break;                                                               \
+        case 128: LAUNCH_TC(CI, 128); break;                                                             \
+        default: toda_set_error("conv_tc_fwd: unsupported cout %d", cout); return TODA_ERR_UNSUPPORTED;  \
     }
+    switch (cin) {
+        case 16: LAUNCH_TC_CO(16); break;
+        case 32: LAUNCH_TC_CO(32); break;
+        case 64: LAUNCH_TC_CO(64); break;
+        case 128: LAUNCH_TC_CO(128); break;
+        default: toda_set_error("conv_tc_fwd: unsupported cin %d", cin); return TODA_ERR_UNSUPPORTED;
+    }
+#undef LAUNCH_TC_CO
 #undef LAUNCH_TC
     TODA_LAUNCH_OK();
     return TODA_OK;
@@ -380,9 +506,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv_tc_wgrad_kernel(const __nv
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int r = rr + 16 * i;
-                    const bool ok = src[i] >= 0;
-                    const __nv_bfloat16 *g = ok ? xb + (size_t)src[i] * CIN + ci : xb;
-                    cp_async_16(a_tile + mb * (kRowsW * 128) + sw128_offset(r, p), g, ok ? 16u : 0u);
+                    const uint32_t dst = a_tile + mb * (kRowsW * 128) + sw128_offset(r, p);
+                    if (src[i] >= 0) cp_async_16(dst, xb + (size_t)src[i] * CIN + ci, 16u);
+                    else st_shared_zero16(dst);
                 }
             }
 #pragma unroll
@@ -392,10 +518,12 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv_tc_wgrad_kernel(const __nv
                 for (int i = 0; i < 4; ++i) {
                     const int r = rr + 16 * i;
                     const bool ok = (row_base + r < r_end) && co < cout;
-                    const __nv_bfloat16 *g = ok ? dyb + (size_t)(row_base + r) * cout + co : dyb;
-                    cp_async_16(b_tile + nb * (kRowsW * 128) + sw128_offset(r, p), g, ok ? 16u : 0u);
+                    const uint32_t dst = b_tile + nb * (kRowsW * 128) + sw128_offset(r, p);
+                    if (ok) cp_async_16(dst, dyb + (size_t)(row_base + r) * cout + co, 16u);
+                    else st_shared_zero16(dst);
                 }
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             cp_async_arrive_noinc(full_bar + 8 * s);
         }
         // epilogue: TMEM lane = M slot (offset, ci); this thread owns one (k, ci) row of every pass
@@ -462,18 +590,26 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv_tc_wgrad_kernel(const __nv
 }
 
 // fixed-order reduction over splits into the parameter layout (Cout, kvol, Cin)
-__global__ void wgrad_tc_reduce_kernel(const float *__restrict__ partial, int splits, int kvol, int cin, int cout,
+__global__ void wgrad_tc_reduce_kernel(const float *__restrict__ partial, int splits, int kvol, int cin, int cpad, int cout,
                                        float *__restrict__ dw_param) {
-    size_t per = (size_t)kvol * cin * cout;
-    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < per; e += (size_t)gridDim.x * blockDim.x) {
-        int ci = (int)(e % cin);
-        size_t t = e / cin;
-        int k = (int)(t % kvol);
-        int co = (int)(t / kvol);
-        size_t src = ((size_t)k * cin + ci) * cout + co;
+    // 8 lanes per output element, each summing every 8th split; combined with a fixed shuffle tree (deterministic)
+    size_t per = (size_t)kvol * cin * cout, per_pad = (size_t)kvol * cpad * cout;
+    const int sub = threadIdx.x & 7;
+    for (size_t e = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 3; e < ((per + 31) & ~(size_t)31);
+         e += ((size_t)gridDim.x * blockDim.x) >> 3) {
         float s = 0.f;
-        for (int sp = 0; sp < splits; ++sp) s += partial[sp * per + src];
-        dw_param[e] = s;
+        if (e < per) {
+            int ci = (int)(e % cin);
+            size_t t = e / cin;
+            int k = (int)(t % kvol);
+            int co = (int)(t / kvol);
+            size_t src = ((size_t)k * cpad + ci) * cout + co;
+            for (int sp = sub; sp < splits; sp += 8) s += partial[sp * per_pad + src];
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (e < per && sub == 0) dw_param[e] = s;
     }
 }
 
@@ -505,16 +641,18 @@ WgradPlan wgrad_plan(int n_in, int n_out, int kvol, int cin, int cout) {
 }  // namespace
 
 bool conv_tc_wgrad_supported(int cin, int cout) {
-    return (cin == 16 || cin == 32 || cin == 64 || cin == 128) && (cout == 16 || cout == 32 || cout == 64 || cout == 128);
+    return ((cin >= 1 && cin <= 16) || cin == 32 || cin == 64 || cin == 128) && (cout == 16 || cout == 32 || cout == 64 || cout == 128);
 }
 
 size_t conv_tc_wgrad_workspace_bytes(int n_in, int n_out, int kvol, int cin, int cout) {
-    WgradPlan p = wgrad_plan(n_in, n_out, kvol, cin, cout);
+    WgradPlan p = wgrad_plan(n_in, n_out, kvol, pad16(cin), cout);
     return p.xb_bytes + p.dyb_bytes + p.partial_bytes + 256;
 }
 
 int conv_tc_wgrad(const float *x, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *dy, int cout,
                   float *dw_param, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+    const int cin_real = cin;
+    cin = pad16(cin);
     WgradPlan p = wgrad_plan(n_in, n_out, kvol, cin, cout);
     size_t need = p.xb_bytes + p.dyb_bytes + p.partial_bytes;
     if (!workspace || workspace_bytes < need) {
@@ -525,7 +663,12 @@ int conv_tc_wgrad(const float *x, int n_in, int cin, const int32_t *nbr, int n_o
     __nv_bfloat16 *dyb = (__nv_bfloat16 *)((char *)workspace + p.xb_bytes);
     float *partial = (float *)((char *)workspace + p.xb_bytes + p.dyb_bytes);
     long long n4 = (long long)n_in * cin / 4;
-    if (n4 > 0) {
+    if (cin_real != cin) {
+        if (n_in > 0) {
+            f32_to_bf16_pad_kernel<<<wave_grid((int64_t)n_in * cin, 256), 256, 0, st>>>(x, n_in, cin_real, cin, xb);
+            TODA_LAUNCH_OK();
+        }
+    } else if (n4 > 0) {
         f32_to_bf16_kernel<<<wave_grid(n4, 256), 256, 0, st>>>(x, n4, xb);
         TODA_LAUNCH_OK();
     }
@@ -549,8 +692,8 @@ int conv_tc_wgrad(const float *x, int n_in, int cin, const int32_t *nbr, int n_o
     }
 #undef LAUNCH_W
     TODA_LAUNCH_OK();
-    size_t per = (size_t)kvol * cin * cout;
-    wgrad_tc_reduce_kernel<<<wave_grid(per, 256), 256, 0, st>>>(partial, p.splits, kvol, cin, cout, dw_param);
+    size_t per = (size_t)kvol * cin_real * cout;
+    wgrad_tc_reduce_kernel<<<wave_grid(per * 8, 256), 256, 0, st>>>(partial, p.splits, kvol, cin_real, cin, cout, dw_param);
     TODA_LAUNCH_OK();
     return TODA_OK;
 }
