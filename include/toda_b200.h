@@ -131,12 +131,15 @@ int toda_rulebook_sparse(const void *index_in, int iD, int iH, int iW, const voi
 int toda_weight_repack(const float *w_param, int kvol, int cin, int cout, int transpose, int mirror_k, float *w_out,
                        void *stream);
 size_t toda_spconv_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol, int precision);
-int toda_spconv_fwd(const float *x, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *w,
-                    int cout, const float *bias, float *y, int precision, void *workspace, size_t workspace_bytes,
-                    void *stream);
+/* x_bf16 / dy_bf16 (optional, may be NULL): an existing bf16 copy of x / dy ([rows][channels], same values rounded to
+ * nearest) that the TODA_CONV_BF16 kernels use instead of converting x / dy themselves. */
+int toda_spconv_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
+                    const float *w, int cout, const float *bias, float *y, int precision, void *workspace,
+                    size_t workspace_bytes, void *stream);
 size_t toda_spconv_wgrad_workspace_bytes(int n_in, int n_out, int kvol, int cin, int cout, int precision);
-int toda_spconv_wgrad(const float *x, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *dy,
-                      int cout, float *dw_param, void *workspace, size_t workspace_bytes, int precision, void *stream);
+int toda_spconv_wgrad(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
+                      const float *dy, const void *dy_bf16, int cout, float *dw_param, void *workspace,
+                      size_t workspace_bytes, int precision, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * K8 BatchNorm1d(eps, momentum) + ReLU (+ residual) over (N_active, C) rows
@@ -153,11 +156,12 @@ int toda_bn_stats(const float *y, int n, int channels, const float *gamma, const
                   float *save_mean, float *save_rstd, void *workspace, size_t workspace_bytes, void *stream);
 int toda_bn_eval_coeffs(const float *gamma, const float *beta, const float *running_mean, const float *running_var,
                         float eps, int channels, float *scale, float *shift, void *stream);
+/* a_bf16 / dy_bf16 (optional, may be NULL): bf16 copies written by the same pass, consumed as tensor-core operands. */
 int toda_bn_apply(const float *y, int n, int channels, const float *scale, const float *shift, const float *residual,
-                  int relu, float *a, void *stream);
+                  int relu, float *a, void *a_bf16, void *stream);
 int toda_bn_bwd(const float *da, const float *a, const float *y, int n, int channels, const float *gamma,
-                const float *save_mean, const float *save_rstd, int relu, int training, float *dy, float *dresidual,
-                float *dgamma, float *dbeta, void *workspace, size_t workspace_bytes, void *stream);
+                const float *save_mean, const float *save_rstd, int relu, int training, float *dy, void *dy_bf16,
+                float *dresidual, float *dgamma, float *dbeta, void *workspace, size_t workspace_bytes, void *stream);
 /* column sums: dbias[c] = sum_rows dy[:,c] */
 int toda_col_sum(const float *dy, int n, int channels, float *out, void *workspace, size_t workspace_bytes,
                  void *stream);

@@ -25,9 +25,13 @@ def bn_act_torch(feat, bn, residual, relu):
     return torch.relu(out) if relu else out
 
 
+def bn_act_tensor_torch(x, bn, residual, relu):
+    return x.replace_feature(bn_act_torch(x.features, bn, residual, relu))
+
+
 def oracle_backbones():
     """The plugin's topology instantiated on the CPU oracle provider (same parameter names, order and init)."""
-    return make_backbones(S, bn_act_torch)
+    return make_backbones(S, bn_act_tensor_torch)
 
 
 def load_golden(name):

@@ -1,6 +1,8 @@
 // K8 BatchNorm1d (+ReLU, +residual) over (N_active, C) rows, and column sums (bias gradient).
 // All passes are HBM-bound streams over (N, C) fp32; reductions use fixed-size per-CTA partials reduced
 // in a fixed order, so results are run-to-run deterministic.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -169,7 +171,8 @@ __global__ void bn_eval_coeffs_kernel(const float *gamma, const float *beta, con
 template <bool VEC>
 __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const float *__restrict__ y, long long total, int c,
                                                             const float *__restrict__ scale, const float *__restrict__ shift,
-                                                            const float *__restrict__ residual, int relu, float *__restrict__ a) {
+                                                            const float *__restrict__ residual, int relu, float *__restrict__ a,
+                                                            __nv_bfloat16 *__restrict__ a_bf16) {
     if (VEC) {
         long long tv = total >> 2;
         for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < tv; e += (long long)gridDim.x * blockDim.x) {
@@ -183,6 +186,13 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const float *__restr
             }
             if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
             ((float4 *)a)[e] = o;
+            if (a_bf16) {   // bf16 shadow for the tensor-core operands of the next convolution
+                __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+                uint2 pk;
+                pk.x = *(uint32_t *)&lo;
+                pk.y = *(uint32_t *)&hi;
+                ((uint2 *)a_bf16)[e] = pk;
+            }
         }
     } else {
         for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -191,6 +201,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const float *__restr
             if (residual) o += __ldg(residual + e);
             if (relu) o = fmaxf(o, 0.f);
             a[e] = o;
+            if (a_bf16) a_bf16[e] = __float2bfloat16_rn(o);
         }
     }
 }
@@ -214,7 +225,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float *__r
                                                                 const float *__restrict__ gamma, const float *__restrict__ mean,
                                                                 const float *__restrict__ rstd, const float *__restrict__ sums,
                                                                 int relu, int training, float *__restrict__ dy,
-                                                                float *__restrict__ dres) {
+                                                                float *__restrict__ dres, __nv_bfloat16 *__restrict__ dy_bf16) {
     float inv_n = n > 0 ? 1.0f / (float)n : 0.f;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         int ch = (int)(e % c);
@@ -231,6 +242,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float *__r
             o = gm * rs * g;
         }
         dy[e] = o;
+        if (dy_bf16) dy_bf16[e] = __float2bfloat16_rn(o);
     }
 }
 
@@ -274,23 +286,23 @@ extern "C" int toda_bn_eval_coeffs(const float *gamma, const float *beta, const 
 }
 
 extern "C" int toda_bn_apply(const float *y, int n, int c, const float *scale, const float *shift, const float *residual,
-                             int relu, float *a, void *stream) {
+                             int relu, float *a, void *a_bf16, void *stream) {
     TODA_CHECK_ARG(n >= 0 && c > 0, "bn_apply: bad sizes");
     if (n == 0) return TODA_OK;
     TODA_CHECK_ARG(y && scale && shift && a, "bn_apply: null pointer");
     long long total = (long long)n * c;
     cudaStream_t st = (cudaStream_t)stream;
     if (c % 4 == 0)
-        bn_apply_kernel<true><<<wave_grid(total / 4, kThreads), kThreads, 0, st>>>(y, total, c, scale, shift, residual, relu, a);
+        bn_apply_kernel<true><<<wave_grid(total / 4, kThreads), kThreads, 0, st>>>(y, total, c, scale, shift, residual, relu, a, (__nv_bfloat16 *)a_bf16);
     else
-        bn_apply_kernel<false><<<wave_grid(total, kThreads), kThreads, 0, st>>>(y, total, c, scale, shift, residual, relu, a);
+        bn_apply_kernel<false><<<wave_grid(total, kThreads), kThreads, 0, st>>>(y, total, c, scale, shift, residual, relu, a, (__nv_bfloat16 *)a_bf16);
     TODA_LAUNCH_OK();
     return TODA_OK;
 }
 
 extern "C" int toda_bn_bwd(const float *da, const float *a, const float *y, int n, int c, const float *gamma,
-                           const float *save_mean, const float *save_rstd, int relu, int training, float *dy, float *dresidual,
-                           float *dgamma, float *dbeta, void *workspace, size_t workspace_bytes, void *stream) {
+                           const float *save_mean, const float *save_rstd, int relu, int training, float *dy, void *dy_bf16,
+                           float *dresidual, float *dgamma, float *dbeta, void *workspace, size_t workspace_bytes, void *stream) {
     TODA_CHECK_ARG(n >= 0 && c > 0 && c <= 256, "bn_bwd: unsupported sizes n=%d c=%d", n, c);
     TODA_CHECK_ARG(save_mean && save_rstd && workspace && (n == 0 || (da && y && dy)) && (!relu || a || n == 0),
                    "bn_bwd: null pointer");
@@ -305,7 +317,7 @@ extern "C" int toda_bn_bwd(const float *da, const float *a, const float *y, int 
     if (n > 0) {
         long long total = (long long)n * c;
         bn_bwd_apply_kernel<<<wave_grid(total, kThreads), kThreads, 0, st>>>(da, a, y, total, c, n, gamma, save_mean, save_rstd,
-                                                                            sums, relu, training, dy, dresidual);
+                                                                            sums, relu, training, dy, dresidual, (__nv_bfloat16 *)dy_bf16);
         TODA_LAUNCH_OK();
     }
     return TODA_OK;

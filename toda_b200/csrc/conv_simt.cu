@@ -5,11 +5,12 @@
 // The tcgen05 path (conv_tc.cu) has the same structure with the accumulator in TMEM.
 #include "common.cuh"
 
-int conv_tc_fwd(const float *x, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *w, int cout,
-                const float *bias, float *y, void *workspace, size_t workspace_bytes, cudaStream_t st);
+int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *w,
+                int cout, const float *bias, float *y, void *workspace, size_t workspace_bytes, cudaStream_t st);
 size_t conv_tc_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol);
-int conv_tc_wgrad(const float *x, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *dy, int cout,
-                  float *dw_param, void *workspace, size_t workspace_bytes, cudaStream_t st);
+int conv_tc_wgrad(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
+                  const float *dy, const void *dy_bf16, int cout, float *dw_param, void *workspace, size_t workspace_bytes,
+                  cudaStream_t st);
 bool conv_tc_supported(int cin, int cout, int kvol);
 bool conv_tc_wgrad_supported(int cin, int cout);
 size_t conv_tc_wgrad_workspace_bytes(int n_in, int n_out, int kvol, int cin, int cout);
@@ -253,7 +254,7 @@ extern "C" size_t toda_spconv_fwd_workspace_bytes(int n_in, int cin, int cout, i
     return 0;
 }
 
-extern "C" int toda_spconv_fwd(const float *x, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
+extern "C" int toda_spconv_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
                                const float *w, int cout, const float *bias, float *y, int precision, void *workspace,
                                size_t workspace_bytes, void *stream) {
     TODA_CHECK_ARG(n_in >= 0 && n_out >= 0 && cin > 0 && cout > 0 && kvol > 0, "spconv_fwd: bad sizes");
@@ -264,7 +265,7 @@ extern "C" int toda_spconv_fwd(const float *x, int n_in, int cin, const int32_t 
     // kernel selection by shape: the tensor-core kernel covers Cin in {<=16 (zero-padded to 16), 32, 64, 128} and
     // Cout in {16,32,64,128}; anything else (e.g. the dgrad of the 4/5-channel input layer) runs on the FFMA kernel.
     if (precision == TODA_CONV_BF16 && conv_tc_supported(cin, cout, kvol))
-        return conv_tc_fwd(x, n_in, cin, nbr, n_out, kvol, w, cout, bias, y, workspace, workspace_bytes, st);
+        return conv_tc_fwd(x, x_bf16, n_in, cin, nbr, n_out, kvol, w, cout, bias, y, workspace, workspace_bytes, st);
     if (cout <= 16) {
         dim3 grid(ceil_div(n_out, 256), ceil_div(cout, 16));
         conv_fwd_f32_kernel<256, 16><<<grid, kThreads, 0, st>>>(x, cin, nbr, n_out, kvol, w, cout, bias, y);
@@ -287,9 +288,9 @@ extern "C" size_t toda_spconv_wgrad_workspace_bytes(int n_in, int n_out, int kvo
     return align_up((size_t)splits * kvol * cin * cout * sizeof(float), 256);
 }
 
-extern "C" int toda_spconv_wgrad(const float *x, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
-                                 const float *dy, int cout, float *dw_param, void *workspace, size_t workspace_bytes,
-                                 int precision, void *stream) {
+extern "C" int toda_spconv_wgrad(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out,
+                                 int kvol, const float *dy, const void *dy_bf16, int cout, float *dw_param, void *workspace,
+                                 size_t workspace_bytes, int precision, void *stream) {
     TODA_CHECK_ARG(n_in >= 0 && n_out >= 0 && cin > 0 && cout > 0 && kvol > 0, "spconv_wgrad: bad sizes");
     TODA_CHECK_ARG(dw_param, "spconv_wgrad: null dw");
     cudaStream_t st = (cudaStream_t)stream;
@@ -300,7 +301,7 @@ extern "C" int toda_spconv_wgrad(const float *x, int n_in, int cin, const int32_
     TODA_CHECK_ARG(x && nbr && dy && workspace, "spconv_wgrad: null pointer");
     TODA_CHECK_ARG(precision == TODA_CONV_FP32 || precision == TODA_CONV_BF16, "spconv_wgrad: unknown precision %d", precision);
     if (precision == TODA_CONV_BF16 && conv_tc_wgrad_supported(cin, cout))
-        return conv_tc_wgrad(x, n_in, cin, nbr, n_out, kvol, dy, cout, dw_param, workspace, workspace_bytes, st);
+        return conv_tc_wgrad(x, x_bf16, n_in, cin, nbr, n_out, kvol, dy, dy_bf16, cout, dw_param, workspace, workspace_bytes, st);
     int splits = wgrad_splits(n_out, kvol, cin, cout);
     size_t need = (size_t)splits * kvol * cin * cout * sizeof(float);
     if (workspace_bytes < need) {

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full_bar + 8 * s, 2 * kProdThreads);   // cp.async completions + releasing arrivals
+            mbar_init(full_bar + 8 * s, kProdThreads / 32);   // one releasing arrival per producer warp
             mbar_init(empty_bar + 8 * s, 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
         const char *xbytes = (const char *)xb + ci_lo * 2;
         const char *wbytes = (const char *)wb + (size_t)rbase * ktot * 2 + p * 16;
         const uint32_t idx_lane = idx_base + 4 * rbase;
+        constexpr int kLag = S - 2;     // chunks a producer runs ahead of its completion signal
         int g = 0, it = 0;              // global chunk counter (stage ring position), tile counter
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int ib = it & 1;
@@ -216,12 +217,25 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
                         else st_shared_zero16(b_dst + j * 4096);
                     }
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // zero stores are generic-proxy writes
-                cp_async_arrive_noinc(full_bar + 8 * s);
-                mbar_arrive(full_bar + 8 * s);
+                // Completion is signalled per WARP, kLag chunks later: 8 arrivals per stage instead of 512 (arrivals
+                // on one mbarrier serialise lane by lane).  wait_group<kLag> returns once this thread's copies of chunk
+                // g-kLag have landed; the proxy fence then also covers that chunk's zero stores.
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                if (g >= kLag) {
+                    asm volatile("cp.async.wait_group %0;" ::"n"(kLag) : "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full_bar + 8 * ((g - kLag) % S));
+                }
             }
             mbar_arrive(idx_empty + 8 * ib);   // this tile's table slice has been consumed
         }
+        // drain: signal the last kLag chunks
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0)
+            for (int j = (g > kLag ? g - kLag : 0); j < g; ++j) mbar_arrive(full_bar + 8 * (j % S));
     } else if (warp == 8) {
         // ------------------------------------------------------------------ MMA issuer (one thread)
         if (lane == 0) {
@@ -357,8 +371,8 @@ size_t conv_tc_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol) {
     return align_up((size_t)n_in * cp * 2 + 16, 256) + align_up((size_t)kvol * cp * cout * 2, 256) + 256;
 }
 
-int conv_tc_fwd(const float *x, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *w, int cout,
-                const float *bias, float *y, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *w,
+                int cout, const float *bias, float *y, void *workspace, size_t workspace_bytes, cudaStream_t st) {
     size_t need = conv_tc_fwd_workspace_bytes(n_in, cin, cout, kvol);
     if (!workspace || workspace_bytes < need) {
         toda_set_error("spconv_fwd(bf16): workspace %zu < required %zu bytes", workspace_bytes, need);
@@ -367,7 +381,9 @@ int conv_tc_fwd(const float *x, int n_in, int cin, const int32_t *nbr, int n_out
     const int cp = pad16(cin);
     __nv_bfloat16 *xb = (__nv_bfloat16 *)workspace;
     __nv_bfloat16 *wb = (__nv_bfloat16 *)((char *)workspace + align_up((size_t)n_in * cp * 2 + 16, 256));
-    if (cp == cin) {
+    if (cp == cin && x_bf16) {
+        xb = (__nv_bfloat16 *)x_bf16;       // caller already holds the bf16 copy (written by the BN-apply pass)
+    } else if (cp == cin) {
         long long n4 = (long long)n_in * cin / 4;
         if (n4 > 0) {
             f32_to_bf16_kernel<<<wave_grid(n4, 256), 256, 0, st>>>(x, n4, xb);
@@ -421,10 +437,14 @@ namespace {
 // 512/NPAD passes resident and owns a slice of the rows (split-K over rows); partial results go to a workspace
 // and are reduced in a fixed order (deterministic) into the parameter layout.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kRowsW = 64;                         // reduction rows per stage
-constexpr int kStagesW = 3;
-constexpr int kStageBytesW = 2 * kRowsW * 128 + 2 * kRowsW * 128;   // A: two 64-wide M blocks; B: up to two N blocks
-constexpr int kSmemW = kStagesW * kStageBytesW + 1024 + 256;
+constexpr int kRowsW = 64;                         // reduction rows per tile (4 UMMA K-steps of 16 rows)
+constexpr int kStagesW = 8;                        // A ring
+constexpr int kATileW = 2 * kRowsW * 128;          // 16 KB: two 64-wide M blocks
+constexpr int kBTileW = 2 * kRowsW * 128;          // 16 KB: up to two 64-wide N blocks
+constexpr int kIdxW = 32 * kRowsW * 4;             // table slice of one row chunk: up to 32 offset slots x 64 rows
+constexpr int kBBufsW = 3;                         // dy tiles in flight (see the lag argument in the producer)
+constexpr int kSmemW = kStagesW * kATileW + kBBufsW * kBTileW + 2 * kIdxW + 1024 + 256;
+constexpr int kWgradThreads = kProdThreads + 32 + 128 + 32;
 
 // MN-major SWIZZLE_128B descriptor: 64 channels (128 B) contiguous, next 64-channel block at `lbo` bytes,
 // groups of 8 rows 1024 B apart.
@@ -438,35 +458,52 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint3
     return d;
 }
 
+// Roles as in the forward kernel: warps 0-7 produce (gather x rows per pass into the A ring; dy rows once per row
+// chunk into a double-buffered B tile), warp 8 issues the MMAs, warps 9-12 drain TMEM at the end, warp 13 streams
+// the table slice of the next row chunk into shared memory.
 template <int CIN, int NPAD>
-__global__ void __launch_bounds__(kThreadsTC, 1) conv_tc_wgrad_kernel(const __nv_bfloat16 *__restrict__ xb,
-                                                                      const int *__restrict__ nbr, int n_out, int kvol,
-                                                                      const __nv_bfloat16 *__restrict__ dyb, int cout,
-                                                                      int rows_per_split, int passes_per_cta,
-                                                                      float *__restrict__ partial) {
+__global__ void __launch_bounds__(kWgradThreads, 1) conv_tc_wgrad_kernel(const __nv_bfloat16 *__restrict__ xb,
+                                                                         const int *__restrict__ nbr, int n_out, int kvol,
+                                                                         const __nv_bfloat16 *__restrict__ dyb, int cout,
+                                                                         int rows_per_split, int passes_per_cta,
+                                                                         float *__restrict__ partial) {
     constexpr int kOffsPerPass = 128 / CIN;
-    constexpr int kMaxPasses = 512 / NPAD;
+    constexpr int S = kStagesW;
     extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = base + kStagesW * kStageBytesW;
-    const uint32_t full_bar = bar_base, empty_bar = bar_base + 8 * kStagesW, accum_bar = bar_base + 16 * kStagesW;
-    const uint32_t tmem_slot = bar_base + 16 * kStagesW + 8;
-    volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *)(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t b_base = base + S * kATileW;
+    const uint32_t idx_base = b_base + kBBufsW * kBTileW;
+    const uint32_t bar_base = idx_base + 2 * kIdxW;
+    const uint32_t a_full = bar_base, a_empty = bar_base + 8 * S;
+    const uint32_t b_full = bar_base + 16 * S, b_empty = b_full + 32;
+    const uint32_t idx_full = b_full + 64, idx_empty = b_full + 80;
+    const uint32_t accum_bar = b_full + 96, tmem_slot = b_full + 104;
+    volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *)(smem_raw + (tmem_slot - raw));
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int split = blockIdx.x, group = blockIdx.y;
     const int total_passes = (kvol + kOffsPerPass - 1) / kOffsPerPass;
     const int pass0 = group * passes_per_cta;
     const int npass = min(passes_per_cta, total_passes - pass0);
+    const int k0 = pass0 * kOffsPerPass;                         // first kernel offset of this CTA
+    const int noffs = min(npass * kOffsPerPass, kvol - k0);      // offsets this CTA really owns
     const int r_begin = split * rows_per_split;
     const int r_end = min(n_out, r_begin + rows_per_split);
     const int nchunks = r_end > r_begin ? (r_end - r_begin + kRowsW - 1) / kRowsW : 0;
-    const int nitems = nchunks * npass;
 
     if (tid == 0) {
-        for (int s = 0; s < kStagesW; ++s) {
-            mbar_init(full_bar + 8 * s, kProducers);
-            mbar_init(empty_bar + 8 * s, 1);
+        for (int s = 0; s < S; ++s) {
+            mbar_init(a_full + 8 * s, kProdThreads / 32);
+            mbar_init(a_empty + 8 * s, 1);
+        }
+        for (int b = 0; b < kBBufsW; ++b) {
+            mbar_init(b_full + 8 * b, kProdThreads / 32);
+            mbar_init(b_empty + 8 * b, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(idx_full + 8 * b, 64);
+            mbar_init(idx_empty + 8 * b, kProdThreads);
         }
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -474,7 +511,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv_tc_wgrad_kernel(const __nv
     // TMEM columns: one [128 x NPAD] accumulator per resident pass, rounded up to a power of two
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < passes_per_cta * NPAD) tmem_cols <<= 1;
-    if (warp == 4) {
+    if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -483,62 +520,144 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv_tc_wgrad_kernel(const __nv
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    if (warp < 4) {
-        const int p = tid & 7, rr = tid >> 3;           // 16-byte piece, row lane (rows rr + 16*i)
-        for (int it = 0; it < nitems; ++it) {
-            const int s = it % kStagesW, use = it / kStagesW;
-            if (use > 0) mbar_wait(empty_bar + 8 * s, (use - 1) & 1);
-            const int rc = it / npass, ps = it - rc * npass;
+    if (warp < 8) {
+        // ------------------------------------------------------------------ producers
+        const int p = tid & 7, rbase = tid >> 3;       // 16-byte piece; rows rbase, rbase + 32
+        const uint32_t piece_off = (uint32_t)(rbase * 128 + ((p ^ (rbase & 7)) << 4));
+        // M slot m = mb*64 + p*8 -> (offset within the pass, channel)
+        //   CIN=128: (0, mb*64+p*8)  CIN=64: (mb, p*8)  CIN=32: (2mb + p/4, (p%4)*8)  CIN=16: (4mb + p/2, (p%2)*8)
+        const int off_lo = CIN >= 64 ? 0 : p / (CIN / 8);
+        const int ci_lo = CIN >= 64 ? p * 8 : (p % (CIN / 8)) * 8;
+        // Completion of item j is signalled kLagW items later (per warp, see the forward kernel).  The dy tile of
+        // chunk rc may only be overwritten once the MMAs of chunk rc-3 are done, and those need the signals of every
+        // item up to (rc-2)*npass-1, the last of which is sent at item (rc-2)*npass-1+kLagW < rc*npass  <=>
+        // kLagW <= 2*npass: holds for npass >= 2; single-pass launches drain at every chunk boundary instead.
+        constexpr int kLagW = 3;
+        int g = 0, signalled = 0;
+        for (int rc = 0; rc < nchunks; ++rc) {
+            const int ib = rc & 1, use_i = rc >> 1;
+            const int bb = rc % kBBufsW, use_b = rc / kBBufsW;
             const int row_base = r_begin + rc * kRowsW;
-            const uint32_t a_tile = base + s * kStageBytesW, b_tile = a_tile + 2 * kRowsW * 128;
-            // A: M slot m = mb*64 + p*8 -> kernel offset and channel of this thread's piece
+            if (npass < 2) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0)
+                    for (; signalled < g; ++signalled) {
+                        if (signalled % npass == 0) mbar_arrive(b_full + 8 * ((signalled / npass) % kBBufsW));
+                        mbar_arrive(a_full + 8 * (signalled % S));
+                    }
+                signalled = g;
+            }
+            // dy rows of this chunk (shared by every pass)
+            if (use_b > 0) mbar_wait(b_empty + 8 * bb, (use_b - 1) & 1);
+            {
+                const uint32_t b_dst = b_base + bb * kBTileW + piece_off;
 #pragma unroll
-            for (int mb = 0; mb < 2; ++mb) {
-                const int m = mb * 64 + p * 8;
-                const int k = (pass0 + ps) * kOffsPerPass + m / CIN, ci = m % CIN;
-                const bool k_ok = k < kvol;
-                int src[4];
+                for (int nb = 0; nb < NPAD / 64; ++nb) {
+                    const int co = nb * 64 + p * 8;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    int r = row_base + rr + 16 * i;
-                    src[i] = (k_ok && r < r_end) ? __ldg(nbr + (size_t)k * n_out + r) : -1;
+                    for (int i = 0; i < 2; ++i) {
+                        const int row = row_base + rbase + 32 * i;
+                        const uint32_t dst = b_dst + nb * 8192 + i * 4096;
+                        if (row < r_end && co < cout) cp_async_16(dst, dyb + (size_t)row * cout + co, 16u);
+                        else st_shared_zero16(dst);
+                    }
                 }
+                // no group commit here: the dy copies join the cp.async group of this chunk's first pass and are
+                // signalled (b_full) together with it
+            }
+            mbar_wait(idx_full + 8 * ib, use_i & 1);
+            const uint32_t idx_tile = idx_base + ib * kIdxW + 4 * rbase;
+            for (int ps = 0; ps < npass; ++ps, ++g) {
+                const int s = g % S, use = g / S;
+                if (use > 0) mbar_wait(a_empty + 8 * s, (use - 1) & 1);
+                const uint32_t a_dst = base + s * kATileW + piece_off;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = rr + 16 * i;
-                    const uint32_t dst = a_tile + mb * (kRowsW * 128) + sw128_offset(r, p);
-                    if (src[i] >= 0) cp_async_16(dst, xb + (size_t)src[i] * CIN + ci, 16u);
-                    else st_shared_zero16(dst);
+                for (int mb = 0; mb < 2; ++mb) {
+                    const int koff = ps * kOffsPerPass + (CIN == 128 ? 0 : (CIN == 64 ? mb : mb * (kOffsPerPass / 2) + off_lo));
+                    const int ci = CIN == 128 ? mb * 64 + ci_lo : ci_lo;
+                    const bool k_ok = koff < noffs;
+                    int src[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        src[i] = -1;
+                        if (k_ok) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(src[i]) : "r"(idx_tile + 4 * (koff * kRowsW + 32 * i)));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const uint32_t dst = a_dst + mb * 8192 + i * 4096;
+                        if (src[i] >= 0) cp_async_16(dst, xb + (size_t)(unsigned)src[i] * CIN + ci, 16u);
+                        else st_shared_zero16(dst);
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                if (g - signalled >= kLagW) {
+                    asm volatile("cp.async.wait_group %0;" ::"n"(kLagW) : "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    const int j = signalled;                     // item whose copies have landed (= g - kLagW)
+                    if (lane == 0) {
+                        if (j % npass == 0) mbar_arrive(b_full + 8 * ((j / npass) % kBBufsW));   // its chunk's dy tile came with it
+                        mbar_arrive(a_full + 8 * (j % S));
+                    }
+                    ++signalled;
                 }
             }
-#pragma unroll
-            for (int nb = 0; nb < NPAD / 64; ++nb) {
-                const int co = nb * 64 + p * 8;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = rr + 16 * i;
-                    const bool ok = (row_base + r < r_end) && co < cout;
-                    const uint32_t dst = b_tile + nb * (kRowsW * 128) + sw128_offset(r, p);
-                    if (ok) cp_async_16(dst, dyb + (size_t)(row_base + r) * cout + co, 16u);
-                    else st_shared_zero16(dst);
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            cp_async_arrive_noinc(full_bar + 8 * s);
+            mbar_arrive(idx_empty + 8 * ib);
         }
-        // epilogue: TMEM lane = M slot (offset, ci); this thread owns one (k, ci) row of every pass
-        if (nitems > 0) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0)
+            for (int j = signalled; j < g; ++j) {
+                if (j % npass == 0) mbar_arrive(b_full + 8 * ((j / npass) % kBBufsW));
+                mbar_arrive(a_full + 8 * (j % S));
+            }
+    } else if (warp == 8) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0 && nchunks > 0) {
+            // D = A(MN-major) x B(MN-major): bits 15 / 16 of the instruction descriptor select MN-major operands
+            constexpr uint32_t idesc = make_idesc_bf16(128, NPAD) | (1u << 15) | (1u << 16);
+            int g = 0;
+            for (int rc = 0; rc < nchunks; ++rc) {
+                const int ib = rc % kBBufsW;
+                mbar_wait(b_full + 8 * ib, (rc / kBBufsW) & 1);
+                const uint32_t b_tile = b_base + ib * kBTileW;
+                for (int ps = 0; ps < npass; ++ps, ++g) {
+                    const int s = g % S, use = g / S;
+                    mbar_wait(a_full + 8 * s, use & 1);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_tile = base + s * kATileW;
+#pragma unroll
+                    for (int j = 0; j < kRowsW / 16; ++j) {     // UMMA K = 16 rows = 2 swizzle atoms of 8 rows
+                        uint64_t ad = make_desc_mn_sw128(a_tile + j * 2048, kRowsW * 128);
+                        uint64_t bd = make_desc_mn_sw128(b_tile + j * 2048, kRowsW * 128);
+                        umma_bf16(tmem_base + ps * NPAD, ad, bd, idesc, (rc | j) != 0);
+                    }
+                    umma_commit(a_empty + 8 * s);
+                }
+                umma_commit(b_empty + 8 * ib);      // dy tile reusable once every pass of this chunk has read it
+            }
+            umma_commit(accum_bar);
+        }
+        __syncwarp();
+    } else if (warp < 13) {
+        // ------------------------------------------------------------------ epilogue: TMEM lane = M slot (offset, ci)
+        const int q = warp & 3;
+        if (nchunks > 0) {
             mbar_wait(accum_bar, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        const int m = warp * 32 + (tid & 31);
+        const int m = q * 32 + lane;
         for (int ps = 0; ps < npass; ++ps) {
             const int k = (pass0 + ps) * kOffsPerPass + m / CIN, ci = m % CIN;
             float *dst = partial + (((size_t)split * kvol + k) * CIN + ci) * cout;
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + ps * NPAD;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ps * NPAD;
             for (int n0 = 0; n0 < cout; n0 += 16) {
                 uint32_t v[16];
-                if (nitems > 0) {
+                if (nchunks > 0) {
                     asm volatile(
                         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
@@ -547,46 +666,38 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv_tc_wgrad_kernel(const __nv
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 } else {
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) v[q] = 0u;      // this split has no rows: its partial is zero
+                    for (int qq = 0; qq < 16; ++qq) v[qq] = 0u;      // this split has no rows: its partial is zero
                 }
                 if (k < kvol) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        *(float4 *)(dst + n0 + 4 * q) = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                                                    __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                    for (int qq = 0; qq < 4; ++qq)
+                        *(float4 *)(dst + n0 + 4 * qq) = make_float4(__uint_as_float(v[4 * qq]), __uint_as_float(v[4 * qq + 1]),
+                                                                     __uint_as_float(v[4 * qq + 2]), __uint_as_float(v[4 * qq + 3]));
                 }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     } else {
-        if ((tid & 31) == 0 && nitems > 0) {
-            // D = A(MN-major) x B(MN-major): bits 15 / 16 of the instruction descriptor select MN-major operands
-            constexpr uint32_t idesc = make_idesc_bf16(128, NPAD) | (1u << 15) | (1u << 16);
-            for (int it = 0; it < nitems; ++it) {
-                const int s = it % kStagesW, use = it / kStagesW;
-                mbar_wait(full_bar + 8 * s, use & 1);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const int rc = it / npass, ps = it - rc * npass;
-                const uint32_t a_tile = base + s * kStageBytesW, b_tile = a_tile + 2 * kRowsW * 128;
-#pragma unroll
-                for (int j = 0; j < kRowsW / 16; ++j) {     // UMMA K = 16 rows = 2 swizzle atoms of 8 rows
-                    uint64_t ad = make_desc_mn_sw128(a_tile + j * 2048, kRowsW * 128);
-                    uint64_t bd = make_desc_mn_sw128(b_tile + j * 2048, kRowsW * 128);
-                    umma_bf16(tmem_base + ps * NPAD, ad, bd, idesc, (rc | j) != 0);
-                }
-                umma_commit(empty_bar + 8 * s);
+        // ------------------------------------------------------------------ indexer (warp 13)
+        for (int rc = 0; rc < nchunks; ++rc) {
+            const int ib = rc & 1, use = rc >> 1;
+            if (use > 0) mbar_wait(idx_empty + 8 * ib, (use - 1) & 1);
+            const uint32_t dst0 = idx_base + ib * kIdxW;
+            const int row_base = r_begin + rc * kRowsW;
+            for (int e = lane; e < noffs * kRowsW; e += 32) {
+                const int koff = e >> 6, r = e & (kRowsW - 1);
+                if (row_base + r < r_end) cp_async_4(dst0 + 4 * e, nbr + (size_t)(k0 + koff) * n_out + row_base + r);
+                else asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst0 + 4 * e), "r"(-1) : "memory");
             }
-            umma_commit(accum_bar);
+            cp_async_arrive_noinc(idx_full + 8 * ib);
+            mbar_arrive(idx_full + 8 * ib);
         }
-        __syncwarp();
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
     }
-    (void)kMaxPasses;
 }
 
 // fixed-order reduction over splits into the parameter layout (Cout, kvol, Cin)
@@ -625,7 +736,8 @@ WgradPlan wgrad_plan(int n_in, int n_out, int kvol, int cin, int cout) {
     int total_passes = (kvol + offs - 1) / offs;
     p.passes_per_cta = total_passes < 512 / npad ? total_passes : 512 / npad;
     p.groups = (total_passes + p.passes_per_cta - 1) / p.passes_per_cta;
-    int want = (2 * kNumSMs + p.groups - 1) / p.groups;
+    int want = kNumSMs / p.groups;   // one resident CTA per SM, a single wave
+    if (want < 1) want = 1;
     int max_by_rows = (n_out + 4 * kRowsW - 1) / (4 * kRowsW);
     p.splits = want < max_by_rows ? want : max_by_rows;
     if (p.splits < 1) p.splits = 1;
@@ -649,8 +761,9 @@ size_t conv_tc_wgrad_workspace_bytes(int n_in, int n_out, int kvol, int cin, int
     return p.xb_bytes + p.dyb_bytes + p.partial_bytes + 256;
 }
 
-int conv_tc_wgrad(const float *x, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *dy, int cout,
-                  float *dw_param, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+int conv_tc_wgrad(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
+                  const float *dy, const void *dy_bf16, int cout, float *dw_param, void *workspace, size_t workspace_bytes,
+                  cudaStream_t st) {
     const int cin_real = cin;
     cin = pad16(cin);
     WgradPlan p = wgrad_plan(n_in, n_out, kvol, cin, cout);
@@ -668,18 +781,24 @@ int conv_tc_wgrad(const float *x, int n_in, int cin, const int32_t *nbr, int n_o
             f32_to_bf16_pad_kernel<<<wave_grid((int64_t)n_in * cin, 256), 256, 0, st>>>(x, n_in, cin_real, cin, xb);
             TODA_LAUNCH_OK();
         }
+    } else if (x_bf16) {
+        xb = (__nv_bfloat16 *)x_bf16;
     } else if (n4 > 0) {
         f32_to_bf16_kernel<<<wave_grid(n4, 256), 256, 0, st>>>(x, n4, xb);
         TODA_LAUNCH_OK();
     }
-    n4 = (long long)n_out * cout / 4;
-    f32_to_bf16_kernel<<<wave_grid(n4, 256), 256, 0, st>>>(dy, n4, dyb);
-    TODA_LAUNCH_OK();
+    if (dy_bf16) {
+        dyb = (__nv_bfloat16 *)dy_bf16;
+    } else {
+        n4 = (long long)n_out * cout / 4;
+        f32_to_bf16_kernel<<<wave_grid(n4, 256), 256, 0, st>>>(dy, n4, dyb);
+        TODA_LAUNCH_OK();
+    }
     dim3 grid(p.splits, p.groups);
 #define LAUNCH_W(CI, NP)                                                                                                  \
     do {                                                                                                                   \
         TODA_CUDA_OK(cudaFuncSetAttribute(conv_tc_wgrad_kernel<CI, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemW)); \
-        conv_tc_wgrad_kernel<CI, NP><<<grid, kThreadsTC, kSmemW, st>>>(xb, nbr, n_out, kvol, dyb, cout, p.rows_per_split,    \
+        conv_tc_wgrad_kernel<CI, NP><<<grid, kWgradThreads, kSmemW, st>>>(xb, nbr, n_out, kvol, dyb, cout, p.rows_per_split,    \
                                                                        p.passes_per_cta, partial);                          \
     } while (0)
     const bool wide = cout > 64;

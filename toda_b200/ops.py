@@ -3,6 +3,7 @@ reference differentiates through the op.  PyTorch is plumbing here (device memor
 graph); every device-side computation is a kernel of libtoda_b200.so.  No CPU fallback.
 """
 import ctypes
+import weakref
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -355,46 +356,70 @@ def rulebook_sparse(index_in: OccupancyIndex, ksize, stride, padding, tag):
 # ------------------------------------------------------------------------------------------------
 # K5-K7 sparse convolution
 # ------------------------------------------------------------------------------------------------
+_repack_cache = {}
+
+
 def _repack(weight, transpose, mirror):
+    """[kvol][Cin][Cout] (or transposed / k-mirrored) copy of a (Cout,kz,ky,kx,Cin) parameter, cached until the
+    parameter is modified (optimizer step bumps ._version)."""
+    key = (id(weight), bool(transpose), bool(mirror))
+    hit = _repack_cache.get(key)
+    if hit is not None and hit[2]() is weight and hit[0] == weight._version and hit[3] == weight.data_ptr():
+        return hit[1]
     cout, kvol, cin = weight.shape[0], weight.shape[1] * weight.shape[2] * weight.shape[3], weight.shape[4]
     out = torch.empty((kvol, cout, cin) if transpose else (kvol, cin, cout), dtype=torch.float32, device=weight.device)
     _C.check(_C.lib().toda_weight_repack(_p(weight), kvol, cin, cout, int(transpose), int(mirror), _p(out), _stream()),
              "toda_weight_repack")
     _count(1)
+    if len(_repack_cache) > 512:
+        _repack_cache.clear()
+    _repack_cache[key] = (weight._version, out, weakref.ref(weight), weight.data_ptr())
     return out
 
 
-def _conv_call(x, cin, nbr, n_out, kvol, w, cout, bias, precision, what="conv_fwd", rb=None):
+def _bf16_shadow_of(t):
+    """bf16 copy attached to a gradient tensor by the BN backward pass (valid only if the tensor was not modified since)."""
+    tag = getattr(t, "_toda_bf16", None)
+    if tag is not None and tag[1] == t._version and tag[0].shape == t.shape:
+        return tag[0]
+    return None
+
+
+def _conv_call(x, xb, cin, nbr, n_out, kvol, w, cout, bias, precision, what="conv_fwd", rb=None):
     y = torch.empty((n_out, cout), dtype=torch.float32, device=x.device)
     L = _C.lib()
     ws_bytes = L.toda_spconv_fwd_workspace_bytes(x.shape[0], cin, cout, kvol, precision)
     ws = _workspace("conv", ws_bytes, x.device) if ws_bytes else None
     with _timed(what, n_in=x.shape[0], n_out=n_out, cin=cin, cout=cout, kvol=kvol, precision=precision, rb=id(rb)):
-        _C.check(L.toda_spconv_fwd(_p(x), x.shape[0], cin, _p(nbr), n_out, kvol, _p(w), cout, _p(bias), _p(y), precision,
-                                   _p(ws), ws.numel() if ws is not None else 0, _stream()), "toda_spconv_fwd")
+        _C.check(L.toda_spconv_fwd(_p(x), _p(xb), x.shape[0], cin, _p(nbr), n_out, kvol, _p(w), cout, _p(bias), _p(y),
+                                   precision, _p(ws), ws.numel() if ws is not None else 0, _stream()), "toda_spconv_fwd")
     _count(1)
     return y
 
 
 class _SparseConv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, rb: Rulebook, precision):
+    def forward(ctx, x, x_bf16, weight, bias, rb: Rulebook, precision):
         x = _need(x.contiguous(), torch.float32, "features")
         weight = _need(weight.contiguous(), torch.float32, "weight")
         cout, cin = weight.shape[0], weight.shape[4]
         assert x.shape == (rb.n_in, cin), (x.shape, rb.n_in, cin)
+        if x_bf16 is not None and (precision != CONV_BF16 or x_bf16.shape != x.shape or x_bf16.dtype != torch.bfloat16
+                                   or not x_bf16.is_contiguous()):
+            x_bf16 = None
         w = _repack(weight, False, False)
         b = bias.contiguous() if bias is not None else None
-        y = _conv_call(x, cin, rb.nbr_fwd, rb.n_out, rb.kvol, w, cout, b, precision, "conv_fwd", rb)
-        ctx.save_for_backward(x, weight)
+        y = _conv_call(x, x_bf16, cin, rb.nbr_fwd, rb.n_out, rb.kvol, w, cout, b, precision, "conv_fwd", rb)
+        ctx.save_for_backward(x, weight, x_bf16)
         ctx.rb, ctx.precision, ctx.has_bias = rb, precision, bias is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
+        x, weight, xb = ctx.saved_tensors
         rb, precision = ctx.rb, ctx.precision
         cout, cin = weight.shape[0], weight.shape[4]
+        dyb = _bf16_shadow_of(dy) if (precision == CONV_BF16 and dy.is_contiguous()) else None
         dy = dy.contiguous()
         L = _C.lib()
         dx = dw = db = None
@@ -402,23 +427,23 @@ class _SparseConv(torch.autograd.Function):
             # dgrad = the same gather-GEMM on the input-stationary table with transposed weights
             wt = _repack(weight, True, rb.subm)
             table = rb.nbr_fwd if rb.subm else rb.nbr_bwd
-            dx = _conv_call(dy, cout, table, rb.n_in, rb.kvol, wt, cin, None, precision, "conv_dgrad", rb)
-        if ctx.needs_input_grad[1]:
+            dx = _conv_call(dy, dyb, cout, table, rb.n_in, rb.kvol, wt, cin, None, precision, "conv_dgrad", rb)
+        if ctx.needs_input_grad[2]:
             dw = torch.empty_like(weight)
             ws_bytes = L.toda_spconv_wgrad_workspace_bytes(rb.n_in, rb.n_out, rb.kvol, cin, cout, precision)
             ws = _workspace("wgrad", ws_bytes, dy.device)
             with _timed("conv_wgrad", n_in=rb.n_in, n_out=rb.n_out, cin=cin, cout=cout, kvol=rb.kvol, precision=precision,
                         rb=id(rb)):
-                _C.check(L.toda_spconv_wgrad(_p(x), rb.n_in, cin, _p(rb.nbr_fwd), rb.n_out, rb.kvol, _p(dy), cout, _p(dw),
-                                             _p(ws), ws.numel(), precision, _stream()), "toda_spconv_wgrad")
+                _C.check(L.toda_spconv_wgrad(_p(x), _p(xb), rb.n_in, cin, _p(rb.nbr_fwd), rb.n_out, rb.kvol, _p(dy), _p(dyb),
+                                             cout, _p(dw), _p(ws), ws.numel(), precision, _stream()), "toda_spconv_wgrad")
             _count(2)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+        if ctx.has_bias and ctx.needs_input_grad[3]:
             db = col_sum(dy)
-        return dx, dw, db, None, None
+        return dx, None, dw, db, None, None
 
 
-def sparse_conv(x, weight, bias, rb, precision=CONV_FP32):
-    return _SparseConv.apply(x, weight, bias, rb, precision)
+def sparse_conv(x, weight, bias, rb, precision=CONV_FP32, x_bf16=None):
+    return _SparseConv.apply(x, x_bf16, weight, bias, rb, precision)
 
 
 def col_sum(t):
@@ -436,7 +461,7 @@ def col_sum(t):
 # ------------------------------------------------------------------------------------------------
 class _BNAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, y, gamma, beta, running_mean, running_var, eps, momentum, training, residual, relu):
+    def forward(ctx, y, gamma, beta, running_mean, running_var, eps, momentum, training, residual, relu, want_bf16):
         y = _need(y.contiguous(), torch.float32, "bn input")
         n, c = y.shape
         dev = y.device
@@ -460,40 +485,49 @@ class _BNAct(torch.autograd.Function):
             rstd = torch.rsqrt(running_var + eps) if y.requires_grad or gamma.requires_grad else None
         res = residual.contiguous() if residual is not None else None
         a = torch.empty_like(y)
+        ab = torch.empty(y.shape, dtype=torch.bfloat16, device=dev) if want_bf16 else None
         with _timed("bn_apply", n=n, c=c, residual=res is not None):
-            _C.check(L.toda_bn_apply(_p(y), n, c, _p(scale), _p(shift), _p(res), int(relu), _p(a), _stream()), "toda_bn_apply")
+            _C.check(L.toda_bn_apply(_p(y), n, c, _p(scale), _p(shift), _p(res), int(relu), _p(a), _p(ab), _stream()),
+                     "toda_bn_apply")
         _count(1)
         ctx.save_for_backward(y, a, gamma, mean, rstd)
-        ctx.cfg = (bool(training), bool(relu), residual is not None)
-        return a
+        ctx.cfg = (bool(training), bool(relu), residual is not None, bool(want_bf16))
+        if ab is not None:
+            ctx.mark_non_differentiable(ab)
+        return a, ab
 
     @staticmethod
-    def backward(ctx, da):
+    def backward(ctx, da, _dab=None):
         y, a, gamma, mean, rstd = ctx.saved_tensors
-        training, relu, has_res = ctx.cfg
+        training, relu, has_res, want_bf16 = ctx.cfg
         n, c = y.shape
         da = da.contiguous()
         L = _C.lib()
         dy = torch.empty_like(y)
+        dyb = torch.empty(y.shape, dtype=torch.bfloat16, device=y.device) if want_bf16 else None
         dres = torch.empty_like(y) if has_res else None
         dgamma = torch.empty((c,), dtype=torch.float32, device=y.device)
         dbeta = torch.empty_like(dgamma)
         ws = _workspace("bn", L.toda_bn_workspace_bytes(c), y.device)
         with _timed("bn_bwd", n=n, c=c, residual=has_res):
             _C.check(L.toda_bn_bwd(_p(da), _p(a), _p(y), n, c, _p(gamma), _p(mean), _p(rstd), int(relu), int(training),
-                                   _p(dy), _p(dres), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _stream()), "toda_bn_bwd")
+                                   _p(dy), _p(dyb), _p(dres), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _stream()),
+                     "toda_bn_bwd")
         _count(3)
-        return dy, dgamma, dbeta, None, None, None, None, None, dres, None
+        if dyb is not None:
+            dy._toda_bf16 = (dyb, dy._version)     # picked up by the producing conv's backward (see _bf16_shadow_of)
+        return dy, dgamma, dbeta, None, None, None, None, None, dres, None, None
 
 
-def bn_act(y, bn: torch.nn.BatchNorm1d, residual=None, relu=True):
+def bn_act(y, bn: torch.nn.BatchNorm1d, residual=None, relu=True, want_bf16=False):
     """BatchNorm1d (+ residual) (+ ReLU) with the module's parameters / running stats
-    (spconv_backbone.py L23-24, L54-64)."""
+    (spconv_backbone.py L23-24, L54-64).  want_bf16: also return the bf16 copy written by the same pass."""
     training = bn.training or bn.running_mean is None
     if training and bn.running_mean is not None and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
-    return _BNAct.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, training, residual,
-                        relu)
+    a, ab = _BNAct.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, training, residual,
+                         relu, want_bf16)
+    return (a, ab) if want_bf16 else a
 
 
 # ------------------------------------------------------------------------------------------------

@@ -39,7 +39,7 @@ STAGES_RES = dict(
 
 def make_backbones(sp, bn_act):
     """sp: module with SparseConvTensor, SparseModule, SparseSequential, SubMConv3d, SparseConv3d.
-    bn_act(features, bn_module, residual, relu) -> features."""
+    bn_act(sparse_tensor, bn_module, residual_features, relu) -> sparse_tensor with the new features."""
     norm_fn = partial(nn.BatchNorm1d, eps=1e-3, momentum=0.01)
 
     class ConvBNReLU(sp.SparseSequential):
@@ -49,8 +49,7 @@ def make_backbones(sp, bn_act):
             super().__init__(conv, norm_fn(channels), nn.ReLU())
 
         def forward(self, x):
-            y = self[0](x)
-            return y.replace_feature(bn_act(y.features, self[1], None, True))
+            return bn_act(self[0](x), self[1], None, True)
 
     class SparseBasicBlock(sp.SparseModule):
         expansion = 1
@@ -66,10 +65,8 @@ def make_backbones(sp, bn_act):
         def forward(self, x):
             if hasattr(x, "canonical"):
                 x = x.canonical()      # the residual rows must line up with the conv outputs
-            out = self.conv1(x)
-            out = out.replace_feature(bn_act(out.features, self.bn1, None, True))
-            out = self.conv2(out)
-            return out.replace_feature(bn_act(out.features, self.bn2, x.features, True))
+            out = bn_act(self.conv1(x), self.bn1, None, True)
+            return bn_act(self.conv2(out), self.bn2, x.features, True)
 
     def build_stage(cin, spec):
         mods = []

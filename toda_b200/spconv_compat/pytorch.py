@@ -41,7 +41,7 @@ def _triple(v):
 
 class SparseConvTensor:
     def __init__(self, features, indices, spatial_shape, batch_size, grid=None, voxel_num=None, indice_dict=None,
-                 benchmark=False, _index=None):
+                 benchmark=False, _index=None, _features_bf16=None):
         self.features = features
         self.indices = indices
         self.spatial_shape = [int(s) for s in spatial_shape]
@@ -51,10 +51,11 @@ class SparseConvTensor:
         self.voxel_num = voxel_num
         self.benchmark = benchmark
         self._index = _index          # ops.OccupancyIndex when rows are in canonical order
+        self._features_bf16 = _features_bf16   # bf16 copy of `features` written by the fused BN pass (tensor-core operand)
 
-    def replace_feature(self, feature):
+    def replace_feature(self, feature, _features_bf16=None):
         return SparseConvTensor(feature, self.indices, self.spatial_shape, self.batch_size, self.grid, self.voxel_num,
-                                self.indice_dict, self.benchmark, self._index)
+                                self.indice_dict, self.benchmark, self._index, _features_bf16)
 
     @property
     def spatial_size(self):
@@ -93,6 +94,15 @@ class SparseConvTensor:
         if not channels_first:
             return out.permute(0, 2, 3, 4, 1).contiguous()
         return out
+
+
+def bn_act_tensor(x, bn, residual, relu):
+    """Fused BatchNorm1d (+residual) (+ReLU) on a SparseConvTensor; in bf16 mode the same pass also writes the bf16
+    copy that the next convolution gathers from."""
+    if _precision == ops.CONV_BF16:
+        a, ab = ops.bn_act(x.features, bn, residual, relu, want_bf16=True)
+        return x.replace_feature(a, ab)
+    return x.replace_feature(ops.bn_act(x.features, bn, residual, relu))
 
 
 class SparseModule(nn.Module):
@@ -136,7 +146,7 @@ class SparseSequential(SparseModule):
                 # BatchNorm1d [+ ReLU] after a conv: one fused pass of libtoda_b200 instead of ATen's
                 if type(m) is nn.BatchNorm1d and m.affine and m.track_running_stats and x.features.is_cuda:
                     relu = i + 1 < len(mods) and type(mods[i + 1]) is nn.ReLU
-                    x = x.replace_feature(ops.bn_act(x.features, m, None, relu))
+                    x = bn_act_tensor(x, m, None, relu)
                     i += 2 if relu else 1
                 else:
                     x = x.replace_feature(m(x.features))
@@ -205,7 +215,7 @@ class SparseConvolution(SparseModule):
         assert isinstance(x, SparseConvTensor)
         x = x.canonical()
         rb, index_out = self._rulebook(x)
-        y = ops.sparse_conv(x.features, self.weight, self.bias, rb, _precision)
+        y = ops.sparse_conv(x.features, self.weight, self.bias, rb, _precision, x._features_bf16)
         return SparseConvTensor(y, rb.out_coords, rb.out_shape, x.batch_size, x.grid, x.voxel_num, x.indice_dict,
                                 x.benchmark, index_out)
 
