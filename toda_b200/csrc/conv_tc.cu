@@ -53,6 +53,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (!done && ++spins > (1u << 24)) __trap();   // a lost arrival must not hang the GPU box
     }
 }
+// non-blocking probe of a barrier phase (used to look one stage ahead while the current MMAs are being issued)
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done;
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -129,7 +150,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
                                                                      const int *__restrict__ nbr, int n_out, int kvol,
                                                                      const __nv_bfloat16 *__restrict__ wb /*[COUT][kvol*CIN]*/,
                                                                      const float *__restrict__ bias, float *__restrict__ y,
-                                                                     int num_tiles) {
+                                                                     int num_tiles, long long *__restrict__ dbg) {
     static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 128, "UMMA N");
     static_assert(CIN == 16 || CIN == 32 || CIN == 64 || CIN == 128, "row = 32..256 bytes of bf16");
     using C = FwdCfg<COUT>;
@@ -227,6 +248,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
                     __syncwarp();
                     if (lane == 0) mbar_arrive(full_bar + 8 * ((g - kLag) % S));
                 }
+                if (dbg && blockIdx.x == 0 && tid == 0 && g < 256) dbg[3 * 256 + g] = clock64();
             }
             mbar_arrive(idx_empty + 8 * ib);   // this tile's table slice has been consumed
         }
@@ -237,33 +259,44 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
         if (lane == 0)
             for (int j = (g > kLag ? g - kLag : 0); j < g; ++j) mbar_arrive(full_bar + 8 * (j % S));
     } else if (warp == 8) {
-        // ------------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer
+        // The whole warp walks the loop (warp-uniform control flow keeps descriptors in uniform registers); one elected
+        // lane issues.  The issuing thread is the serial bottleneck of small-N layers, so the next stage's barrier is
+        // probed (non-blocking) before the current chunk's MMAs are issued: its latency overlaps the issue.
+        {
             constexpr uint32_t idesc = make_idesc_bf16(kTileM, COUT);
             int g = 0, it = 0;
+            uint32_t ready = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
                 const int ab = it & 1, ause = it >> 1;
                 if (ause > 0) mbar_wait(acc_empty + 8 * ab, (ause - 1) & 1);   // epilogue has drained this accumulator
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + ab * COUT;
                 for (int c = 0; c < nchunks; ++c, ++g) {
                     const int s = g % S, use = g / S;
-                    mbar_wait(full_bar + 8 * s, use & 1);
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    if (dbg && blockIdx.x == 0 && lane == 0 && g < 256) dbg[4 * 256 + g] = clock64();
+                    if (!ready) mbar_wait(full_bar + 8 * s, use & 1);
+                    if (dbg && blockIdx.x == 0 && lane == 0 && g < 256) dbg[5 * 256 + g] = clock64();
+                    const int sn = (g + 1) % S, usen = (g + 1) / S;
+                    ready = mbar_test(full_bar + 8 * sn, usen & 1);            // look one stage ahead
+                    // (the producers fence their generic-proxy zero stores before signalling; no proxy fence needed here)
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_tile = base + s * C::kStage, b_tile = a_tile + kABytes;
                     const int ksteps = min(kChunkK, ktot - c * kChunkK) / 16;     // UMMA K = 16 bf16 = 32 bytes
-                    for (int j = 0; j < ksteps; ++j) {
-                        uint64_t ad = make_desc_k_sw128(a_tile + j * 32);
-                        uint64_t bd = make_desc_k_sw128(b_tile + j * 32);
-                        umma_bf16(d_tmem, ad, bd, idesc, (c | j) != 0);
+                    if (elect_one()) {
+                        for (int j = 0; j < ksteps; ++j) {
+                            uint64_t ad = make_desc_k_sw128(a_tile + j * 32);
+                            uint64_t bd = make_desc_k_sw128(b_tile + j * 32);
+                            umma_bf16(d_tmem, ad, bd, idesc, (c | j) != 0);
+                        }
+                        umma_commit(empty_bar + 8 * s);        // stage reusable once these MMAs have read it
                     }
-                    umma_commit(empty_bar + 8 * s);        // stage reusable once these MMAs have read it
+                    __syncwarp();
+                    if (dbg && blockIdx.x == 0 && lane == 0 && g < 256) dbg[6 * 256 + g] = clock64();
                 }
-                umma_commit(acc_full + 8 * ab);            // accumulator of this tile complete
+                if (elect_one()) umma_commit(acc_full + 8 * ab);            // accumulator of this tile complete
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else if (warp < 13) {
         // ------------------------------------------------------------------ epilogue (warps 9..12)
         const int q = warp & 3;                                  // TMEM lane quarter this warp may access
@@ -361,6 +394,13 @@ __global__ void weight_to_kmajor_bf16_kernel(const float *__restrict__ w, int kv
 
 static inline int pad16(int c) { return c < 16 ? 16 : c; }
 
+int conv_tma_fwd(const void *xb, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const void *wb, int cout,
+                 const float *bias, float *y, cudaStream_t st);
+
+// development aid: device buffer (7 x 256 clock64 samples) filled by CTA 0 of the cp.async forward kernel
+static long long *g_dbg_timeline = nullptr;
+extern "C" void toda_debug_set_timeline(long long *buf) { g_dbg_timeline = buf; }
+
 bool conv_tc_supported(int cin, int cout, int kvol) {
     bool cin_ok = (cin >= 1 && cin < 16) || cin == 16 || cin == 32 || cin == 64 || cin == 128;
     return cin_ok && kvol <= kMaxKvol && (cout == 16 || cout == 32 || cout == 64 || cout == 128);
@@ -396,12 +436,20 @@ int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int
     weight_to_kmajor_bf16_kernel<<<wave_grid((int64_t)kvol * cp * cout, 256), 256, 0, st>>>(w, kvol, cin, cp, cout, wb);
     TODA_LAUNCH_OK();
     cin = cp;
+    // operand feed, chosen by shape from measurements on B200 (profiles/r01_feed_ab.md): TMA (gather4 rows + tiled
+    // weights, conv_tma.cu) wins when rows are 256 bytes (Cin = Cout = 128); gather4 costs ~20-50 cycles per instruction
+    // whatever the row width, so the cp.async producers below are faster for narrower rows.
+    // TODA_TC_FEED=tma|cpasync forces one of them (A/B measurements).
+    static int feed = -1;
+    if (feed < 0) { const char *e = getenv("TODA_TC_FEED"); feed = !e ? 2 : (e[0] == 'c' ? 0 : 1); }
+    if (feed == 1 || (feed == 2 && cin == 128 && cout == 128))
+        return conv_tma_fwd(xb, n_in, cin, nbr, n_out, kvol, wb, cout, bias, y, st);
     int num_tiles = ceil_div(n_out, kTileM);
     int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;   // persistent: one CTA per SM walks the tiles
 #define LAUNCH_TC(CI, CO)                                                                                                    \
     do {                                                                                                                     \
         TODA_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_kernel<CI, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<CO>::kSmem)); \
-        conv_tc_fwd_kernel<CI, CO><<<grid, kFwdThreads, FwdCfg<CO>::kSmem, st>>>(xb, nbr, n_out, kvol, wb, bias, y, num_tiles); \
+        conv_tc_fwd_kernel<CI, CO><<<grid, kFwdThreads, FwdCfg<CO>::kSmem, st>>>(xb, nbr, n_out, kvol, wb, bias, y, num_tiles, g_dbg_timeline); \
     } while (0)
 #define LAUNCH_TC_CO(CI)                                                                                 \
     switch (cout) {                                                                                      \
@@ -615,34 +663,39 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_tc_wgrad_kernel(const _
                 mbar_arrive(a_full + 8 * (j % S));
             }
     } else if (warp == 8) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0 && nchunks > 0) {
+        // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
+        if (nchunks > 0) {
             // D = A(MN-major) x B(MN-major): bits 15 / 16 of the instruction descriptor select MN-major operands
             constexpr uint32_t idesc = make_idesc_bf16(128, NPAD) | (1u << 15) | (1u << 16);
             int g = 0;
+            uint32_t ready = 0;
             for (int rc = 0; rc < nchunks; ++rc) {
                 const int ib = rc % kBBufsW;
                 mbar_wait(b_full + 8 * ib, (rc / kBBufsW) & 1);
                 const uint32_t b_tile = b_base + ib * kBTileW;
                 for (int ps = 0; ps < npass; ++ps, ++g) {
                     const int s = g % S, use = g / S;
-                    mbar_wait(a_full + 8 * s, use & 1);
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    if (!ready) mbar_wait(a_full + 8 * s, use & 1);
+                    ready = mbar_test(a_full + 8 * ((g + 1) % S), ((g + 1) / S) & 1);   // look one stage ahead
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_tile = base + s * kATileW;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int j = 0; j < kRowsW / 16; ++j) {     // UMMA K = 16 rows = 2 swizzle atoms of 8 rows
-                        uint64_t ad = make_desc_mn_sw128(a_tile + j * 2048, kRowsW * 128);
-                        uint64_t bd = make_desc_mn_sw128(b_tile + j * 2048, kRowsW * 128);
-                        umma_bf16(tmem_base + ps * NPAD, ad, bd, idesc, (rc | j) != 0);
+                        for (int j = 0; j < kRowsW / 16; ++j) {     // UMMA K = 16 rows = 2 swizzle atoms of 8 rows
+                            uint64_t ad = make_desc_mn_sw128(a_tile + j * 2048, kRowsW * 128);
+                            uint64_t bd = make_desc_mn_sw128(b_tile + j * 2048, kRowsW * 128);
+                            umma_bf16(tmem_base + ps * NPAD, ad, bd, idesc, (rc | j) != 0);
+                        }
+                        umma_commit(a_empty + 8 * s);
                     }
-                    umma_commit(a_empty + 8 * s);
+                    __syncwarp();
                 }
-                umma_commit(b_empty + 8 * ib);      // dy tile reusable once every pass of this chunk has read it
+                if (elect_one()) umma_commit(b_empty + 8 * ib);      // dy tile reusable once every pass of this chunk has read it
+                __syncwarp();
             }
-            umma_commit(accum_bar);
+            if (elect_one()) umma_commit(accum_bar);
+            __syncwarp();
         }
-        __syncwarp();
     } else if (warp < 13) {
         // ------------------------------------------------------------------ epilogue: TMEM lane = M slot (offset, ci)
         const int q = warp & 3;
