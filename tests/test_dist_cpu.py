@@ -1,0 +1,52 @@
+"""World-size-2 gloo test (CPU) of the data-parallel host logic: frame sharding and the flat-bucket gradient
+all-reduce that replaces DistributedDataParallel on the hot path (tools/stage1_cutmix_train.py L142)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from toda_b200.dist import FlatGradBucket, shard_frames
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+    bucket = FlatGradBucket(net.parameters())
+    # every parameter's .grad is a view into the flat buffer
+    assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in net.parameters())
+    for step in range(2):
+        bucket.zero()
+        x = torch.full((4, 5), float(rank + 1 + step))
+        net(x).sum().backward()
+        local = bucket.flat.clone()
+        bucket.all_reduce_mean()
+        gathered = [torch.zeros_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        assert torch.allclose(bucket.flat, sum(gathered) / world, rtol=1e-6, atol=1e-7)
+        assert torch.equal(torch.cat([p.grad.flatten() for p in net.parameters()]), bucket.flat)
+    first = shard_frames(100, 4, rank)
+    out[rank] = (first, float(bucket.flat.sum()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_world2():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    assert out[0][0] == 100 and out[1][0] == 104            # disjoint frame ranges per rank
+    assert abs(out[0][1] - out[1][1]) < 1e-6                # identical averaged gradients on both ranks
