@@ -220,29 +220,70 @@ __global__ void bn_bwd_finalize_kernel(const double *__restrict__ partial, int n
 }
 
 // dy = gamma*rstd*(g - sum_g/N - xhat*sum_gx/N)   (training)   |   dy = gamma*rstd*g   (eval)
+// Per channel this is dy = A*g + B*y + C with A = gamma*rstd, B = -gamma*rstd^2*sum_gx/N,
+// C = -A*sum_g/N - B*mean: coefficients are computed once per thread (4 channels), rows stream as float4.
+template <bool VEC>
 __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float *__restrict__ da, const float *__restrict__ a,
                                                                 const float *__restrict__ y, long long total, int c, int n,
                                                                 const float *__restrict__ gamma, const float *__restrict__ mean,
                                                                 const float *__restrict__ rstd, const float *__restrict__ sums,
                                                                 int relu, int training, float *__restrict__ dy,
                                                                 float *__restrict__ dres, __nv_bfloat16 *__restrict__ dy_bf16) {
-    float inv_n = n > 0 ? 1.0f / (float)n : 0.f;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        int ch = (int)(e % c);
-        float g = __ldg(da + e);
-        if (relu && !(__ldg(a + e) > 0.f)) g = 0.f;
-        if (dres) dres[e] = g;
-        float gm = gamma ? gamma[ch] : 1.f;
-        float rs = rstd[ch];
-        float o;
-        if (training) {
-            float xh = (__ldg(y + e) - mean[ch]) * rs;
-            o = gm * rs * (g - sums[ch] * inv_n - xh * sums[c + ch] * inv_n);
-        } else {
-            o = gm * rs * g;
+    const float inv_n = n > 0 ? 1.0f / (float)n : 0.f;
+    if (VEC) {
+        const long long tv = total >> 2;
+        const long long stride = (long long)gridDim.x * blockDim.x;      // multiple of c/4 (host guarantees it)
+        long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+        const int ch = (int)((e << 2) % c);
+        float A[4], B[4], C[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float gm = gamma ? gamma[ch + q] : 1.f, rs = rstd[ch + q];
+            A[q] = gm * rs;
+            B[q] = training ? -gm * rs * rs * sums[c + ch + q] * inv_n : 0.f;
+            C[q] = training ? -A[q] * sums[ch + q] * inv_n - B[q] * mean[ch + q] : 0.f;
         }
-        dy[e] = o;
-        if (dy_bf16) dy_bf16[e] = __float2bfloat16_rn(o);
+        for (; e < tv; e += stride) {
+            float4 g4 = __ldg((const float4 *)da + e);
+            float4 y4 = training ? __ldg((const float4 *)y + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (relu) {
+                float4 a4 = __ldg((const float4 *)a + e);
+                g4.x = a4.x > 0.f ? g4.x : 0.f; g4.y = a4.y > 0.f ? g4.y : 0.f;
+                g4.z = a4.z > 0.f ? g4.z : 0.f; g4.w = a4.w > 0.f ? g4.w : 0.f;
+            }
+            if (dres) ((float4 *)dres)[e] = g4;
+            float4 o;
+            o.x = fmaf(A[0], g4.x, fmaf(B[0], y4.x, C[0]));
+            o.y = fmaf(A[1], g4.y, fmaf(B[1], y4.y, C[1]));
+            o.z = fmaf(A[2], g4.z, fmaf(B[2], y4.z, C[2]));
+            o.w = fmaf(A[3], g4.w, fmaf(B[3], y4.w, C[3]));
+            ((float4 *)dy)[e] = o;
+            if (dy_bf16) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+                uint2 pk;
+                pk.x = *(uint32_t *)&lo;
+                pk.y = *(uint32_t *)&hi;
+                ((uint2 *)dy_bf16)[e] = pk;
+            }
+        }
+    } else {
+        for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+            int ch = (int)(e % c);
+            float g = __ldg(da + e);
+            if (relu && !(__ldg(a + e) > 0.f)) g = 0.f;
+            if (dres) dres[e] = g;
+            float gm = gamma ? gamma[ch] : 1.f;
+            float rs = rstd[ch];
+            float o;
+            if (training) {
+                float xh = (__ldg(y + e) - mean[ch]) * rs;
+                o = gm * rs * (g - sums[ch] * inv_n - xh * sums[c + ch] * inv_n);
+            } else {
+                o = gm * rs * g;
+            }
+            dy[e] = o;
+            if (dy_bf16) dy_bf16[e] = __float2bfloat16_rn(o);
+        }
     }
 }
 
@@ -316,8 +357,12 @@ extern "C" int toda_bn_bwd(const float *da, const float *a, const float *y, int 
     TODA_LAUNCH_OK();
     if (n > 0) {
         long long total = (long long)n * c;
-        bn_bwd_apply_kernel<<<wave_grid(total, kThreads), kThreads, 0, st>>>(da, a, y, total, c, n, gamma, save_mean, save_rstd,
-                                                                            sums, relu, training, dy, dresidual, (__nv_bfloat16 *)dy_bf16);
+        if (c % 4 == 0 && kThreads % (c / 4) == 0)   // grid*block is then a multiple of c/4: a thread keeps its 4 channels
+            bn_bwd_apply_kernel<true><<<wave_grid(total / 4, kThreads), kThreads, 0, st>>>(
+                da, a, y, total, c, n, gamma, save_mean, save_rstd, sums, relu, training, dy, dresidual, (__nv_bfloat16 *)dy_bf16);
+        else
+            bn_bwd_apply_kernel<false><<<wave_grid(total, kThreads), kThreads, 0, st>>>(
+                da, a, y, total, c, n, gamma, save_mean, save_rstd, sums, relu, training, dy, dresidual, (__nv_bfloat16 *)dy_bf16);
         TODA_LAUNCH_OK();
     }
     return TODA_OK;

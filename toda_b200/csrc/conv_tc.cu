@@ -283,11 +283,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
                     const uint32_t a_tile = base + s * C::kStage, b_tile = a_tile + kABytes;
                     const int ksteps = min(kChunkK, ktot - c * kChunkK) / 16;     // UMMA K = 16 bf16 = 32 bytes
                     if (elect_one()) {
-                        for (int j = 0; j < ksteps; ++j) {
-                            uint64_t ad = make_desc_k_sw128(a_tile + j * 32);
-                            uint64_t bd = make_desc_k_sw128(b_tile + j * 32);
-                            umma_bf16(d_tmem, ad, bd, idesc, (c | j) != 0);
-                        }
+                        // one descriptor per operand per chunk; a K-step advances the start-address field by 32 B (>>4 = 2)
+                        const uint64_t ad0 = make_desc_k_sw128(a_tile), bd0 = make_desc_k_sw128(b_tile);
+                        umma_bf16(d_tmem, ad0, bd0, idesc, c != 0);
+                        for (int j = 1; j < ksteps; ++j) umma_bf16(d_tmem, ad0 + 2 * j, bd0 + 2 * j, idesc, 1u);
                         umma_commit(empty_bar + 8 * s);        // stage reusable once these MMAs have read it
                     }
                     __syncwarp();
