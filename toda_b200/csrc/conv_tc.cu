@@ -484,13 +484,17 @@ namespace {
 // 512/NPAD passes resident and owns a slice of the rows (split-K over rows); partial results go to a workspace
 // and are reduced in a fixed order (deterministic) into the parameter layout.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kRowsW = 64;                         // reduction rows per tile (4 UMMA K-steps of 16 rows)
-constexpr int kStagesW = 8;                        // A ring
-constexpr int kATileW = 2 * kRowsW * 128;          // 16 KB: two 64-wide M blocks
-constexpr int kBTileW = 2 * kRowsW * 128;          // 16 KB: up to two 64-wide N blocks
-constexpr int kIdxW = 32 * kRowsW * 4;             // table slice of one row chunk: up to 32 offset slots x 64 rows
-constexpr int kBBufsW = 3;                         // dy tiles in flight (see the lag argument in the producer)
-constexpr int kSmemW = kStagesW * kATileW + kBBufsW * kBTileW + 2 * kIdxW + 1024 + 256;
+// Per-launch geometry of the wgrad kernel.  ROWS = reduction rows per item (ROWS/16 UMMA K-steps): 128 for N <= 64
+// (small-N MMAs are cheap, so the per-item barrier / issue overhead dominates and bigger items pay), 64 for N = 128.
+template <int NPAD, int ROWS> struct WCfg {
+    static constexpr int kATile = 2 * ROWS * 128;              // two 64-wide M blocks
+    static constexpr int kBTile = (NPAD / 64) * ROWS * 128;    // one or two 64-wide N blocks
+    static constexpr int kIdx = 32 * ROWS * 4;                 // table slice of one row chunk: <= 32 offset slots
+    static constexpr int kBBufs = ROWS == 128 ? 2 : 3;         // dy tiles in flight
+    static constexpr int kStages = ROWS == 128 ? 4 : 8;        // A ring
+    static constexpr int kLag = ROWS == 128 ? 2 : 3;           // items a producer runs ahead of its completion signal
+    static constexpr int kSmem = kStages * kATile + kBBufs * kBTile + 2 * kIdx + 1024 + 256;
+};
 constexpr int kWgradThreads = kProdThreads + 32 + 128 + 32;
 
 // MN-major SWIZZLE_128B descriptor: 64 channels (128 B) contiguous, next 64-channel block at `lbo` bytes,
@@ -508,14 +512,17 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint3
 // Roles as in the forward kernel: warps 0-7 produce (gather x rows per pass into the A ring; dy rows once per row
 // chunk into a double-buffered B tile), warp 8 issues the MMAs, warps 9-12 drain TMEM at the end, warp 13 streams
 // the table slice of the next row chunk into shared memory.
-template <int CIN, int NPAD>
+template <int CIN, int NPAD, int ROWS>
 __global__ void __launch_bounds__(kWgradThreads, 1) conv_tc_wgrad_kernel(const __nv_bfloat16 *__restrict__ xb,
                                                                          const int *__restrict__ nbr, int n_out, int kvol,
                                                                          const __nv_bfloat16 *__restrict__ dyb, int cout,
                                                                          int rows_per_split, int passes_per_cta,
                                                                          float *__restrict__ partial) {
+    using W = WCfg<NPAD, ROWS>;
     constexpr int kOffsPerPass = 128 / CIN;
-    constexpr int S = kStagesW;
+    constexpr int S = W::kStages;
+    constexpr int kRowsW = ROWS, kATileW = W::kATile, kBTileW = W::kBTile, kIdxW = W::kIdx, kBBufsW = W::kBBufs;
+    constexpr int kRowIters = ROWS / 32;            // rows per producer thread per 64-wide block
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -579,13 +586,13 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_tc_wgrad_kernel(const _
         // chunk rc may only be overwritten once the MMAs of chunk rc-3 are done, and those need the signals of every
         // item up to (rc-2)*npass-1, the last of which is sent at item (rc-2)*npass-1+kLagW < rc*npass  <=>
         // kLagW <= 2*npass: holds for npass >= 2; single-pass launches drain at every chunk boundary instead.
-        constexpr int kLagW = 3;
+        constexpr int kLagW = W::kLag;       // (2 dy buffers: kLagW <= npass; 3 buffers: kLagW <= 2*npass)
         int g = 0, signalled = 0;
         for (int rc = 0; rc < nchunks; ++rc) {
             const int ib = rc & 1, use_i = rc >> 1;
             const int bb = rc % kBBufsW, use_b = rc / kBBufsW;
             const int row_base = r_begin + rc * kRowsW;
-            if (npass < 2) {
+            if (npass < kLagW) {
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
@@ -604,9 +611,9 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_tc_wgrad_kernel(const _
                 for (int nb = 0; nb < NPAD / 64; ++nb) {
                     const int co = nb * 64 + p * 8;
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
+                    for (int i = 0; i < kRowIters; ++i) {
                         const int row = row_base + rbase + 32 * i;
-                        const uint32_t dst = b_dst + nb * 8192 + i * 4096;
+                        const uint32_t dst = b_dst + nb * (kRowsW * 128) + i * 4096;
                         if (row < r_end && co < cout) cp_async_16(dst, dyb + (size_t)row * cout + co, 16u);
                         else st_shared_zero16(dst);
                     }
@@ -625,15 +632,15 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_tc_wgrad_kernel(const _
                     const int koff = ps * kOffsPerPass + (CIN == 128 ? 0 : (CIN == 64 ? mb : mb * (kOffsPerPass / 2) + off_lo));
                     const int ci = CIN == 128 ? mb * 64 + ci_lo : ci_lo;
                     const bool k_ok = koff < noffs;
-                    int src[2];
+                    int src[kRowIters];
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
+                    for (int i = 0; i < kRowIters; ++i) {
                         src[i] = -1;
                         if (k_ok) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(src[i]) : "r"(idx_tile + 4 * (koff * kRowsW + 32 * i)));
                     }
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const uint32_t dst = a_dst + mb * 8192 + i * 4096;
+                    for (int i = 0; i < kRowIters; ++i) {
+                        const uint32_t dst = a_dst + mb * (kRowsW * 128) + i * 4096;
                         if (src[i] >= 0) cp_async_16(dst, xb + (size_t)(unsigned)src[i] * CIN + ci, 16u);
                         else st_shared_zero16(dst);
                     }
@@ -680,11 +687,11 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_tc_wgrad_kernel(const _
                     const uint32_t a_tile = base + s * kATileW;
                     if (elect_one()) {
 #pragma unroll
-                        for (int j = 0; j < kRowsW / 16; ++j) {     // UMMA K = 16 rows = 2 swizzle atoms of 8 rows
-                            uint64_t ad = make_desc_mn_sw128(a_tile + j * 2048, kRowsW * 128);
-                            uint64_t bd = make_desc_mn_sw128(b_tile + j * 2048, kRowsW * 128);
-                            umma_bf16(tmem_base + ps * NPAD, ad, bd, idesc, (rc | j) != 0);
-                        }
+                        // UMMA K = 16 rows = 2 swizzle atoms of 8 rows = 2048 B: a K-step adds 128 to the start-address field
+                        const uint64_t ad0 = make_desc_mn_sw128(a_tile, kRowsW * 128), bd0 = make_desc_mn_sw128(b_tile, kRowsW * 128);
+                        umma_bf16(tmem_base + ps * NPAD, ad0, bd0, idesc, rc != 0);
+                        for (int j = 1; j < kRowsW / 16; ++j)
+                            umma_bf16(tmem_base + ps * NPAD, ad0 + 128 * j, bd0 + 128 * j, idesc, 1u);
                         umma_commit(a_empty + 8 * s);
                     }
                     __syncwarp();
@@ -737,7 +744,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_tc_wgrad_kernel(const _
             const uint32_t dst0 = idx_base + ib * kIdxW;
             const int row_base = r_begin + rc * kRowsW;
             for (int e = lane; e < noffs * kRowsW; e += 32) {
-                const int koff = e >> 6, r = e & (kRowsW - 1);
+                const int koff = e / kRowsW, r = e & (kRowsW - 1);
                 if (row_base + r < r_end) cp_async_4(dst0 + 4 * e, nbr + (size_t)(k0 + koff) * n_out + row_base + r);
                 else asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst0 + 4 * e), "r"(-1) : "memory");
             }
@@ -784,6 +791,7 @@ struct WgradPlan {
 WgradPlan wgrad_plan(int n_in, int n_out, int kvol, int cin, int cout) {
     WgradPlan p;
     int npad = cout <= 64 ? 64 : 128;
+    const int kRowsW = npad == 64 ? 128 : 64;
     int offs = 128 / cin;
     int total_passes = (kvol + offs - 1) / offs;
     p.passes_per_cta = total_passes < 512 / npad ? total_passes : 512 / npad;
@@ -847,18 +855,19 @@ int conv_tc_wgrad(const float *x, const void *x_bf16, int n_in, int cin, const i
         TODA_LAUNCH_OK();
     }
     dim3 grid(p.splits, p.groups);
-#define LAUNCH_W(CI, NP)                                                                                                  \
+#define LAUNCH_W(CI, NP, RW)                                                                                              \
     do {                                                                                                                   \
-        TODA_CUDA_OK(cudaFuncSetAttribute(conv_tc_wgrad_kernel<CI, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemW)); \
-        conv_tc_wgrad_kernel<CI, NP><<<grid, kWgradThreads, kSmemW, st>>>(xb, nbr, n_out, kvol, dyb, cout, p.rows_per_split,    \
-                                                                       p.passes_per_cta, partial);                          \
+        constexpr int smem = WCfg<NP, RW>::kSmem;                                                                          \
+        TODA_CUDA_OK(cudaFuncSetAttribute(conv_tc_wgrad_kernel<CI, NP, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        conv_tc_wgrad_kernel<CI, NP, RW><<<grid, kWgradThreads, smem, st>>>(xb, nbr, n_out, kvol, dyb, cout, p.rows_per_split,  \
+                                                                           p.passes_per_cta, partial);                      \
     } while (0)
     const bool wide = cout > 64;
     switch (cin) {
-        case 16: if (wide) LAUNCH_W(16, 128); else LAUNCH_W(16, 64); break;
-        case 32: if (wide) LAUNCH_W(32, 128); else LAUNCH_W(32, 64); break;
-        case 64: if (wide) LAUNCH_W(64, 128); else LAUNCH_W(64, 64); break;
-        case 128: if (wide) LAUNCH_W(128, 128); else LAUNCH_W(128, 64); break;
+        case 16: if (wide) LAUNCH_W(16, 128, 64); else LAUNCH_W(16, 64, 128); break;
+        case 32: if (wide) LAUNCH_W(32, 128, 64); else LAUNCH_W(32, 64, 128); break;
+        case 64: if (wide) LAUNCH_W(64, 128, 64); else LAUNCH_W(64, 64, 128); break;
+        case 128: if (wide) LAUNCH_W(128, 128, 64); else LAUNCH_W(128, 64, 128); break;
         default: toda_set_error("conv_tc_wgrad: unsupported cin %d", cin); return TODA_ERR_UNSUPPORTED;
     }
 #undef LAUNCH_W
