@@ -309,17 +309,33 @@ def roofline_from_profile(prof, bd, peaks, step_ms):
                 row["gbs"] = round(g["bytes"] / (g["ms"] * 1e-3) / 1e9, 1)
                 row["frac_of_hbm_peak"] = round(row["gbs"] / peaks["hbm_gbs"], 4)
         layers.append(row)
-    top_key, top = max(groups.items(), key=lambda kv: kv[1]["ms"])
+    # dominant KERNEL (device function): forward and dgrad convolutions are the same tcgen05 kernel
+    # (conv_tc_fwd_kernel / conv_tma_fwd_kernel), the weight gradient is conv_tc_wgrad_kernel
+    fams = defaultdict(lambda: dict(ms=0.0, calls=0, flops=0.0, bytes=0.0, kind="hbm"))
+    for key, g in groups.items():
+        fam = ("conv_tc_fwd_kernel (fwd + dgrad, all layers)" if key.startswith(("conv_fwd", "conv_dgrad")) else
+               "conv_tc_wgrad_kernel (all layers)" if key.startswith("conv_wgrad") else key)
+        f = fams[fam]
+        for k in ("ms", "calls", "flops", "bytes"):
+            f[k] += g[k]
+        f["kind"] = g.get("kind", "hbm")
+    top_key, top = max(fams.items(), key=lambda kv: kv[1]["ms"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")      # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(top_key.split(" ")[0])
     if top.get("kind") == "conv":
-        achieved = top["flops"] / top["calls"] / (top["ms"] / top["calls"] * 1e-3) / 1e12
+        achieved = top["flops"] / (top["ms"] * 1e-3) / 1e12
         roof = dict(bound="tensor", kernel=top_key, achieved=achieved, peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s",
-                    frac=achieved / peaks["bf16_tflops_sustained"], traffic=None, peak_source=peaks["source"] + ", sustained bf16",
-                    launches=top["calls"], avg_launch_ms=top["ms"] / top["calls"], share_of_step=top["ms"] / step_ms)
+                    frac=achieved / peaks["bf16_tflops_sustained"], traffic=traffic,
+                    peak_source=peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                    launches=top["calls"], avg_launch_ms=top["ms"] / top["calls"], share_of_step=top["ms"] / step_ms,
+                    flops_per_launch=top["flops"] / top["calls"], algorithmic_bytes_per_launch=top["bytes"] / top["calls"])
     else:
-        achieved = top["bytes"] / top["calls"] / (top["ms"] / top["calls"] * 1e-3) / 1e9
+        achieved = top["bytes"] / (top["ms"] * 1e-3) / 1e9
         roof = dict(bound="hbm", kernel=top_key, achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"],
-                    traffic=None, peak_source=peaks["source"], launches=top["calls"], avg_launch_ms=top["ms"] / top["calls"],
-                    share_of_step=top["ms"] / step_ms)
+                    traffic=traffic, peak_source=peaks["source"], launches=top["calls"], avg_launch_ms=top["ms"] / top["calls"],
+                    share_of_step=top["ms"] / step_ms, algorithmic_bytes_per_launch=top["bytes"] / top["calls"])
     return roof, layers
 
 

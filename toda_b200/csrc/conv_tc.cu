@@ -129,13 +129,18 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int p) { return (uint32_
 constexpr int kProdThreads = 256;
 constexpr int kFwdThreads = kProdThreads + 32 + 128 + 32;   // 448
 constexpr int kFwdSmemBudget = 200 * 1024;
-template <int COUT> struct FwdCfg {
-    static constexpr int kBBytes = COUT * kChunkK * 2;
-    static constexpr int kStage = kABytes + kBBytes;
+// KB = 64-element K blocks per chunk.  Small-N MMAs are cheap, so the per-chunk barrier round trip and issue overhead
+// dominate: layers with Cout <= 64 use KB = 2 (8 MMAs per round trip), Cout = 128 keeps KB = 1 (more stages).
+template <int COUT, int KB> struct FwdCfg {
+    static constexpr int kABlock = kTileM * kChunkK * 2;     // 16 KB per K block
+    static constexpr int kBBlock = COUT * kChunkK * 2;
+    static constexpr int kATile = KB * kABlock, kBTile = KB * kBBlock;
+    static constexpr int kStage = kATile + kBTile;
     static constexpr int kStagesRaw = (kFwdSmemBudget - 2 * kIdxBytes) / kStage;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
     static constexpr int kSmem = kStages * kStage + 1024 + 256 + 2 * kIdxBytes;
     static constexpr int kTmemCols = 2 * COUT < 32 ? 32 : 2 * COUT;
+    static_assert(kStages >= 3, "need at least 3 stages");
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -145,7 +150,7 @@ __device__ __forceinline__ void cp_async_4(uint32_t dst, const void *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, int KB>
 __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_bfloat16 *__restrict__ xb,
                                                                      const int *__restrict__ nbr, int n_out, int kvol,
                                                                      const __nv_bfloat16 *__restrict__ wb /*[COUT][kvol*CIN]*/,
@@ -153,8 +158,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
                                                                      int num_tiles, long long *__restrict__ dbg) {
     static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 128, "UMMA N");
     static_assert(CIN == 16 || CIN == 32 || CIN == 64 || CIN == 128, "row = 32..256 bytes of bf16");
-    using C = FwdCfg<COUT>;
+    using C = FwdCfg<COUT, KB>;
     constexpr int S = C::kStages;
+    constexpr int kChunkElems = KB * kChunkK;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
@@ -168,7 +174,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ktot = kvol * CIN;
-    const int nchunks = (ktot + kChunkK - 1) / kChunkK;
+    const int nchunks = (ktot + kChunkElems - 1) / kChunkElems;
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
@@ -215,27 +221,32 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
             for (int c = 0; c < nchunks; ++c, ++g) {
                 const int s = g % S, use = g / S;
                 if (use > 0) mbar_wait(empty_bar + 8 * s, (use - 1) & 1);
-                const uint32_t a_dst = base + s * C::kStage + piece_off, b_dst = a_dst + kABytes;
-                const int k = CIN == 128 ? (c >> 1) : c * kOffsPerChunk + k_sub;
-                const bool k_ok = k < kvol;      // only the K tail of CIN=16/32 layers can miss
-                const int ci_hi = CIN == 128 ? (c & 1) * 64 : 0;
-                int src[4];
+                const uint32_t a_dst0 = base + s * C::kStage + piece_off, b_dst0 = a_dst0 + C::kATile;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    src[i] = -1;
-                    if (k_ok) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(src[i]) : "r"(idx_tile + 4 * (k * kTileM + 32 * i)));
-                }
+                for (int kb = 0; kb < KB; ++kb) {
+                    const int cb = c * KB + kb;                       // 64-element block index on the flattened K axis
+                    const uint32_t a_dst = a_dst0 + kb * C::kABlock, b_dst = b_dst0 + kb * C::kBBlock;
+                    const int k = CIN == 128 ? (cb >> 1) : cb * kOffsPerChunk + k_sub;
+                    const bool k_ok = k < kvol;      // only the K tail can miss
+                    const int ci_hi = CIN == 128 ? (cb & 1) * 64 : 0;
+                    int src[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    // missing neighbour: plain zero store (a zero-size cp.async would still send a request per piece)
-                    if (src[i] >= 0) cp_async_16(a_dst + i * 4096, xbytes + ((size_t)(unsigned)src[i] * CIN + ci_hi) * 2, 16u);
-                    else st_shared_zero16(a_dst + i * 4096);
-                }
+                    for (int i = 0; i < 4; ++i) {
+                        src[i] = -1;
+                        if (k_ok) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(src[i]) : "r"(idx_tile + 4 * (k * kTileM + 32 * i)));
+                    }
 #pragma unroll
-                for (int j = 0; j < (COUT + 31) / 32; ++j) {
-                    if (rbase + 32 * j < COUT) {
-                        if (k_ok) cp_async_16(b_dst + j * 4096, wbytes + ((size_t)j * 32 * ktot + (size_t)c * kChunkK) * 2, 16u);
-                        else st_shared_zero16(b_dst + j * 4096);
+                    for (int i = 0; i < 4; ++i) {
+                        // missing neighbour: plain zero store (a zero-size cp.async would still send a request per piece)
+                        if (src[i] >= 0) cp_async_16(a_dst + i * 4096, xbytes + ((size_t)(unsigned)src[i] * CIN + ci_hi) * 2, 16u);
+                        else st_shared_zero16(a_dst + i * 4096);
+                    }
+#pragma unroll
+                    for (int j = 0; j < (COUT + 31) / 32; ++j) {
+                        if (rbase + 32 * j < COUT) {
+                            if (k_ok) cp_async_16(b_dst + j * 4096, wbytes + ((size_t)j * 32 * ktot + (size_t)cb * kChunkK) * 2, 16u);
+                            else st_shared_zero16(b_dst + j * 4096);
+                        }
                     }
                 }
                 // Completion is signalled per WARP, kLag chunks later: 8 arrivals per stage instead of 512 (arrivals
@@ -280,13 +291,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
                     ready = mbar_test(full_bar + 8 * sn, usen & 1);            // look one stage ahead
                     // (the producers fence their generic-proxy zero stores before signalling; no proxy fence needed here)
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_tile = base + s * C::kStage, b_tile = a_tile + kABytes;
-                    const int ksteps = min(kChunkK, ktot - c * kChunkK) / 16;     // UMMA K = 16 bf16 = 32 bytes
+                    const uint32_t a_tile = base + s * C::kStage, b_tile = a_tile + C::kATile;
+                    const int ksteps = min(kChunkElems, ktot - c * kChunkElems) / 16;     // UMMA K = 16 bf16 = 32 bytes
                     if (elect_one()) {
-                        // one descriptor per operand per chunk; a K-step advances the start-address field by 32 B (>>4 = 2)
+                        // one descriptor per operand per chunk; a K-step advances the start-address field by 32 B (>>4 = 2),
+                        // the second 64-element K block starts one A / B block further
                         const uint64_t ad0 = make_desc_k_sw128(a_tile), bd0 = make_desc_k_sw128(b_tile);
                         umma_bf16(d_tmem, ad0, bd0, idesc, c != 0);
-                        for (int j = 1; j < ksteps; ++j) umma_bf16(d_tmem, ad0 + 2 * j, bd0 + 2 * j, idesc, 1u);
+                        for (int j = 1; j < ksteps; ++j) {
+                            const uint32_t blk = j >> 2, st = j & 3;
+                            umma_bf16(d_tmem, ad0 + blk * (C::kABlock >> 4) + 2 * st, bd0 + blk * (C::kBBlock >> 4) + 2 * st, idesc, 1u);
+                        }
                         umma_commit(empty_bar + 8 * s);        // stage reusable once these MMAs have read it
                     }
                     __syncwarp();
@@ -447,8 +462,10 @@ int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int
     int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;   // persistent: one CTA per SM walks the tiles
 #define LAUNCH_TC(CI, CO)                                                                                                    \
     do {                                                                                                                     \
-        TODA_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_kernel<CI, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg<CO>::kSmem)); \
-        conv_tc_fwd_kernel<CI, CO><<<grid, kFwdThreads, FwdCfg<CO>::kSmem, st>>>(xb, nbr, n_out, kvol, wb, bias, y, num_tiles, g_dbg_timeline); \
+        constexpr int KB_ = (CO) <= 64 ? 2 : 1;                                                                              \
+        constexpr int smem = FwdCfg<CO, KB_>::kSmem;                                                                         \
+        TODA_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_kernel<CI, CO, KB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        conv_tc_fwd_kernel<CI, CO, KB_><<<grid, kFwdThreads, smem, st>>>(xb, nbr, n_out, kvol, wb, bias, y, num_tiles, g_dbg_timeline); \
     } while (0)
 #define LAUNCH_TC_CO(CI)                                                                                 \
     switch (cout) {                                                                                      \
