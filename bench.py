@@ -59,49 +59,75 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region through NVML (a polling thread; a concurrent
+    `nvidia-smi -lms` process was seen to stall the driver for tens of ms inside single steps).  Falls back to one
+    nvidia-smi query if NVML cannot be loaded."""
 
-    def __init__(self, index):
-        self.rows, self.proc = [], None
+    def __init__(self, index, period_s=0.02):
+        self.sm, self.max_sm, self.reasons, self.nv = [], None, set(), None
+        self._stop = threading.Event()
+        self.recording = False        # the thread polls from start-up (NVML's first calls are slow); samples count only
+                                      # between begin() and stop(), i.e. inside the timed region
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            phys, vis = index, os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            parts = [x.strip() for x in vis.split(",")] if vis else []
+            if parts and all(x.isdigit() for x in parts) and index < len(parts):
+                phys = int(parts[index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.period = period_s
+            self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.nv = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _poll(self):
+        nv = self.nv
+        names = {getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap"}
+        while not self._stop.is_set():
+            try:
+                clk = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                if self.recording:
+                    self.sm.append(clk)
+                    for bit, nm in names.items():
+                        if mask & bit:
+                            self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def begin(self):
+        self.recording = True
 
     def stop(self):
-        if self.proc is None:
-            return None
-        self.proc.terminate()
+        self.recording = False
+        if self.nv is not None:
+            self._stop.set()
+            self.t.join(timeout=1.0)
+            if self.sm:
+                return dict(sm_mhz=float(np.median(self.sm)), sm_max_mhz=self.max_sm, reasons=sorted(self.reasons),
+                            samples=len(self.sm), source="nvml")
         try:
-            self.proc.wait(timeout=2)
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            out = subprocess.check_output(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits"], text=True,
+                                          timeout=10).strip().splitlines()[0]
+            f = [x.strip() for x in out.split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return dict(sm_mhz=float(f[0]), sm_max_mhz=float(f[1]), samples=1, source="nvidia-smi (after the timed region)",
+                        reasons=[n for n, v in zip(names, f[2:6]) if v.lower().startswith("active")])
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, f[2:6]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
             return None
-        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -145,11 +171,17 @@ def run_ours(args, rank, world, local_rank):
     devs = [(p.to(device), o.to(device)) for p, o in hosts]
     cot = None
 
+    trace = [] if os.environ.get("TODA_BENCH_TRACE") else None
+
     def step(points, offsets, reduce=True):
         nonlocal cot
+        t0 = time.perf_counter()
         bucket.zero()
         bd = {"points": points, "point_frame_offsets": offsets, "batch_size": FRAMES_PER_GPU}
-        bd = hc(net(vfe(bd)))
+        bd = vfe(bd)
+        t1 = time.perf_counter()
+        bd = hc(net(bd))
+        t2 = time.perf_counter()
         sf = bd["spatial_features"]
         if cot is None:
             cot = torch.randn(sf.shape, device=device, generator=torch.Generator(device=device).manual_seed(1)) / sf.numel()
@@ -157,6 +189,9 @@ def run_ours(args, rank, world, local_rank):
         loss.backward()
         if reduce:
             bucket.all_reduce_mean()
+        if trace is not None:
+            t3 = time.perf_counter()
+            trace.append((round((t1 - t0) * 1e3, 2), round((t2 - t1) * 1e3, 2), round((t3 - t2) * 1e3, 2)))
         return loss, bd
 
     def barrier():
@@ -168,6 +203,7 @@ def run_ours(args, rank, world, local_rank):
     # priming (untimed, before the W warm-up steps): reserve a large cached block once (row counts differ from batch to
     # batch, and the caching allocator must never fall back to a device-synchronising cudaMalloc / cudaFree in a timed
     # step), then every pooled batch twice so that workspace growth and cudaFuncSetAttribute are behind us
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     reserve = torch.empty(24 << 30, dtype=torch.uint8, device=device)
     del reserve
     for i in range(2 * POOL):
@@ -175,9 +211,10 @@ def run_ours(args, rank, world, local_rank):
     for i in range(args.warmup):
         step(*devs[i % POOL])
     barrier()
-    gc.collect()
-    gc.disable()      # no cyclic-GC pauses inside the timed regions (re-enabled after the e2e arm)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    gc.collect()      # (the cyclic GC stays enabled: with it disabled, step garbage pins ~5 GB of activations per step and
+                      # the allocator falls back to cudaMalloc -- measured as 20-130 ms stalls in the second timed step)
+    if sampler:
+        sampler.begin()
     ops.reset_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
@@ -192,6 +229,9 @@ def run_ours(args, rank, world, local_rank):
     per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
     if rank == 0:
         print("per-step ms (device arm): " + " ".join("%.2f" % t for t in per_step), file=sys.stderr)
+        if trace is not None:
+            print("host ms per step (vfe, fwd, bwd) of the timed steps: " + " ".join(str(t) for t in trace[-args.steps:]),
+                  file=sys.stderr)
     ms = e0.elapsed_time(e1)
     launches = ops.launches()
     t = torch.tensor([ms], device=device)
@@ -213,7 +253,6 @@ def run_ours(args, rank, world, local_rank):
         e2e_step(i)
     e1.record()
     barrier()
-    gc.enable()
     t = torch.tensor([e0.elapsed_time(e1)], device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -25,17 +25,17 @@ def _worker(rank, world, port, out):
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
     bucket = FlatGradBucket(net.parameters())
-    # every parameter's .grad is a view into the flat buffer
-    assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in net.parameters())
     for step in range(2):
         bucket.zero()
+        assert all(p.grad is None for p in net.parameters())
         x = torch.full((4, 5), float(rank + 1 + step))
         net(x).sum().backward()
-        local = bucket.flat.clone()
+        local = torch.cat([p.grad.flatten() for p in net.parameters()]).clone()
         bucket.all_reduce_mean()
         gathered = [torch.zeros_like(local) for _ in range(world)]
         dist.all_gather(gathered, local)
         assert torch.allclose(bucket.flat, sum(gathered) / world, rtol=1e-6, atol=1e-7)
+        # the averaged gradients are back in every parameter's .grad
         assert torch.equal(torch.cat([p.grad.flatten() for p in net.parameters()]), bucket.flat)
     first = shard_frames(100, 4, rank)
     out[rank] = (first, float(bucket.flat.sum()))

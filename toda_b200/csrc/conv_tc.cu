@@ -16,6 +16,7 @@
 //
 // No scatter and no atomics: every output row is written once.  dgrad is the same kernel on the
 // input-stationary table with transposed weights.
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -76,6 +77,15 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
 }
 __device__ __forceinline__ void st_shared_zero16(uint32_t dst) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
@@ -153,7 +163,7 @@ __device__ __forceinline__ void cp_async_4(uint32_t dst, const void *src) {
 template <int CIN, int COUT, int KB>
 __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_bfloat16 *__restrict__ xb,
                                                                      const int *__restrict__ nbr, int n_out, int kvol,
-                                                                     const __nv_bfloat16 *__restrict__ wb /*[COUT][kvol*CIN]*/,
+                                                                     const __grid_constant__ CUtensorMap map_w /*[COUT][kvol*CIN] bf16*/,
                                                                      const float *__restrict__ bias, float *__restrict__ y,
                                                                      int num_tiles, long long *__restrict__ dbg) {
     static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 128, "UMMA N");
@@ -178,7 +188,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full_bar + 8 * s, kProdThreads / 32);   // one releasing arrival per producer warp
+            // one releasing arrival per producer warp (gathered A rows, cp.async) + one arrive.expect_tx for the weight
+            // tile, which the TMA writes and completes by transaction bytes
+            mbar_init(full_bar + 8 * s, kProdThreads / 32 + 1);
             mbar_init(empty_bar + 8 * s, 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -210,7 +222,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
         const int k_sub = CIN >= 64 ? 0 : p / (CIN / 8);
         const int ci_lo = CIN >= 64 ? p * 8 : (p % (CIN / 8)) * 8;
         const char *xbytes = (const char *)xb + ci_lo * 2;
-        const char *wbytes = (const char *)wb + (size_t)rbase * ktot * 2 + p * 16;
         const uint32_t idx_lane = idx_base + 4 * rbase;
         constexpr int kLag = S - 2;     // chunks a producer runs ahead of its completion signal
         int g = 0, it = 0;              // global chunk counter (stage ring position), tile counter
@@ -221,11 +232,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
             for (int c = 0; c < nchunks; ++c, ++g) {
                 const int s = g % S, use = g / S;
                 if (use > 0) mbar_wait(empty_bar + 8 * s, (use - 1) & 1);
-                const uint32_t a_dst0 = base + s * C::kStage + piece_off, b_dst0 = a_dst0 + C::kATile;
+                const uint32_t a_dst0 = base + s * C::kStage + piece_off;
 #pragma unroll
                 for (int kb = 0; kb < KB; ++kb) {
                     const int cb = c * KB + kb;                       // 64-element block index on the flattened K axis
-                    const uint32_t a_dst = a_dst0 + kb * C::kABlock, b_dst = b_dst0 + kb * C::kBBlock;
+                    const uint32_t a_dst = a_dst0 + kb * C::kABlock;
                     const int k = CIN == 128 ? (cb >> 1) : cb * kOffsPerChunk + k_sub;
                     const bool k_ok = k < kvol;      // only the K tail can miss
                     const int ci_hi = CIN == 128 ? (cb & 1) * 64 : 0;
@@ -241,13 +252,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
                         if (src[i] >= 0) cp_async_16(a_dst + i * 4096, xbytes + ((size_t)(unsigned)src[i] * CIN + ci_hi) * 2, 16u);
                         else st_shared_zero16(a_dst + i * 4096);
                     }
-#pragma unroll
-                    for (int j = 0; j < (COUT + 31) / 32; ++j) {
-                        if (rbase + 32 * j < COUT) {
-                            if (k_ok) cp_async_16(b_dst + j * 4096, wbytes + ((size_t)j * 32 * ktot + (size_t)cb * kChunkK) * 2, 16u);
-                            else st_shared_zero16(b_dst + j * 4096);
-                        }
-                    }
+                }
+                // weights of this chunk: one TMA tile per K block ([COUT rows][64] bf16, hardware SWIZZLE_128B; the part of
+                // the box beyond K = kvol*CIN is zero-filled by the TMA)
+                if (tid == 0) {
+                    const int left = ktot - c * kChunkElems;                       // K elements left from this chunk on
+                    const int nblk = left >= kChunkElems ? KB : (left + kChunkK - 1) / kChunkK;   // blocks that hold data
+                    mbar_arrive_expect_tx(full_bar + 8 * s, nblk * C::kBBlock);
+                    const uint32_t b_tile = base + s * C::kStage + C::kATile;
+                    for (int kb = 0; kb < nblk; ++kb)
+                        tma_load_2d(b_tile + kb * C::kBBlock, &map_w, (c * KB + kb) * kChunkK, 0, full_bar + 8 * s);
                 }
                 // Completion is signalled per WARP, kLag chunks later: 8 arrivals per stage instead of 512 (arrivals
                 // on one mbarrier serialise lane by lane).  wait_group<kLag> returns once this thread's copies of chunk
@@ -410,6 +424,8 @@ static inline int pad16(int c) { return c < 16 ? 16 : c; }
 
 int conv_tma_fwd(const void *xb, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const void *wb, int cout,
                  const float *bias, float *y, cudaStream_t st);
+// 2-D bf16 row-major tensor map [rows][cols] with box [box_rows][box_cols], swizzle by box row bytes (conv_tma.cu)
+int conv_tma_make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols);
 
 // development aid: device buffer (7 x 256 clock64 samples) filled by CTA 0 of the cp.async forward kernel
 static long long *g_dbg_timeline = nullptr;
@@ -460,12 +476,14 @@ int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int
         return conv_tma_fwd(xb, n_in, cin, nbr, n_out, kvol, wb, cout, bias, y, st);
     int num_tiles = ceil_div(n_out, kTileM);
     int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;   // persistent: one CTA per SM walks the tiles
+    CUtensorMap map_w;
+    if (int rc = conv_tma_make_map(&map_w, wb, (uint64_t)cout, (uint64_t)kvol * cin, (uint32_t)cout, kChunkK)) return rc;
 #define LAUNCH_TC(CI, CO)                                                                                                    \
     do {                                                                                                                     \
         constexpr int KB_ = (CO) <= 64 ? 2 : 1;                                                                              \
         constexpr int smem = FwdCfg<CO, KB_>::kSmem;                                                                         \
         TODA_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_kernel<CI, CO, KB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        conv_tc_fwd_kernel<CI, CO, KB_><<<grid, kFwdThreads, smem, st>>>(xb, nbr, n_out, kvol, wb, bias, y, num_tiles, g_dbg_timeline); \
+        conv_tc_fwd_kernel<CI, CO, KB_><<<grid, kFwdThreads, smem, st>>>(xb, nbr, n_out, kvol, map_w, bias, y, num_tiles, g_dbg_timeline); \
     } while (0)
 #define LAUNCH_TC_CO(CI)                                                                                 \
     switch (cout) {                                                                                      \

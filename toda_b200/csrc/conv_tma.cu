@@ -348,6 +348,10 @@ int launch(const __nv_bfloat16 *xb, int n_in, const int32_t *nbr, int n_out, int
 
 }  // namespace
 
+int conv_tma_make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
+    return make_map(m, ptr, rows, cols, box_rows, box_cols);
+}
+
 // xb: bf16 [n_in][cin], wb: bf16 [cout][kvol*cin]; cin, cout in {16,32,64,128}
 int conv_tma_fwd(const void *xb, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const void *wb, int cout,
                  const float *bias, float *y, cudaStream_t st) {

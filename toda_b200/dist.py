@@ -15,24 +15,26 @@ def shard_frames(global_first_frame, frames_per_rank, rank):
 
 
 class FlatGradBucket:
-    """Views every parameter's .grad into one contiguous buffer so that the step's collective is a single
-    all-reduce with no flatten / unflatten copies."""
+    """One flat buffer for the step's only collective.  Gradients are produced by autograd into fresh tensors
+    (p.grad is reset to None every step, so no accumulate kernels run); `all_reduce_mean` packs them with one
+    concatenation, all-reduces the flat buffer once over NCCL and scatters the averages back in place."""
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
         total = sum(p.numel() for p in self.params)
         p0 = self.params[0]
         self.flat = torch.zeros(total, dtype=p0.dtype, device=p0.device)
-        off = 0
-        for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        self.views = list(torch.split(self.flat, [p.numel() for p in self.params]))
 
     def zero(self):
-        self.flat.zero_()
+        for p in self.params:
+            p.grad = None
 
     def all_reduce_mean(self, group=None):
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+        torch.cat([g.reshape(-1) for g in grads], out=self.flat)
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
         self.flat.div_(dist.get_world_size(group))
+        torch._foreach_copy_([g.view(-1) for g in grads], self.views)
