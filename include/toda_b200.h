@@ -133,8 +133,12 @@ int toda_weight_repack(const float *w_param, int kvol, int cin, int cout, int tr
 size_t toda_spconv_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol, int precision);
 /* x_bf16 / dy_bf16 (optional, may be NULL): an existing bf16 copy of x / dy ([rows][channels], same values rounded to
  * nearest) that the TODA_CONV_BF16 kernels use instead of converting x / dy themselves. */
+/* bn_sums (optional, may be NULL; tensor-core kernel only, see toda_spconv_uses_tensor_cores): double[2*cout] receiving
+ * sum(y) and sum(y*y) per output channel, accumulated in the epilogue, for toda_bn_finalize_sums -- the BatchNorm that
+ * follows the convolution (spconv_backbone.py L23-24) then needs no statistics pass over y. */
+int toda_spconv_uses_tensor_cores(int cin, int cout, int kvol, int precision);
 int toda_spconv_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
-                    const float *w, int cout, const float *bias, float *y, int precision, void *workspace,
+                    const float *w, int cout, const float *bias, float *y, double *bn_sums, int precision, void *workspace,
                     size_t workspace_bytes, void *stream);
 size_t toda_spconv_wgrad_workspace_bytes(int n_in, int n_out, int kvol, int cin, int cout, int precision);
 int toda_spconv_wgrad(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
@@ -154,6 +158,9 @@ size_t toda_bn_workspace_bytes(int channels);
 int toda_bn_stats(const float *y, int n, int channels, const float *gamma, const float *beta, float eps,
                   float momentum, float *running_mean, float *running_var, float *scale, float *shift,
                   float *save_mean, float *save_rstd, void *workspace, size_t workspace_bytes, void *stream);
+int toda_bn_finalize_sums(const double *sums, int n, int channels, const float *gamma, const float *beta, float eps,
+                          float momentum, float *running_mean, float *running_var, float *scale, float *shift,
+                          float *save_mean, float *save_rstd, void *stream);
 int toda_bn_eval_coeffs(const float *gamma, const float *beta, const float *running_mean, const float *running_var,
                         float eps, int channels, float *scale, float *shift, void *stream);
 /* a_bf16 / dy_bf16 (optional, may be NULL): bf16 copies written by the same pass, consumed as tensor-core operands. */

@@ -27,11 +27,12 @@ __global__ void __launch_bounds__(kThreads) col_reduce_vec_kernel(const float *_
     if (MODE == 1) { m4 = __ldg((const float4 *)mean + tx); r4 = __ldg((const float4 *)rstd + tx); }
     const long long stride = (long long)gridDim.x * rpi;
     const bool active = ty < rpi;
-    for (long long r = (long long)blockIdx.x * rpi + ty; active && r < n; r += 4 * stride) {
-        float4 v0[4], v1[4], v2[4];
-        bool ok[4];
+    constexpr int U = 4;                          // rows in flight per thread and array
+    for (long long r = (long long)blockIdx.x * rpi + ty; active && r < n; r += U * stride) {
+        float4 v0[U], v1[U], v2[U];
+        bool ok[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             long long rr = r + u * stride;
             ok[u] = rr < n;
             size_t e = ok[u] ? (size_t)rr * tpr + tx : 0;
@@ -39,7 +40,7 @@ __global__ void __launch_bounds__(kThreads) col_reduce_vec_kernel(const float *_
             if (MODE == 1) { v1[u] = __ldg((const float4 *)p1 + e); v2[u] = __ldg((const float4 *)p2 + e); }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             if (!ok[u]) continue;
             float x[4] = {v0[u].x, v0[u].y, v0[u].z, v0[u].w};
             if (MODE == 0) {
@@ -313,6 +314,18 @@ extern "C" int toda_bn_stats(const float *y, int n, int c, const float *gamma, c
     TODA_LAUNCH_OK();
     bn_finalize_kernel<<<ceil_div(c * 32, 128), 128, 0, st>>>(partial, kPartials, n, c, gamma, beta, eps, momentum, running_mean,
                                                         running_var, scale, shift, save_mean, save_rstd);
+    TODA_LAUNCH_OK();
+    return TODA_OK;
+}
+
+extern "C" int toda_bn_finalize_sums(const double *sums, int n, int c, const float *gamma, const float *beta, float eps,
+                                     float momentum, float *running_mean, float *running_var, float *scale, float *shift,
+                                     float *save_mean, float *save_rstd, void *stream) {
+    TODA_CHECK_ARG(n >= 0 && c > 0 && sums && scale && shift, "bn_finalize_sums: bad args");
+    // `sums` = [sum(y) per channel | sum(y*y) per channel]: the layout of one partial block of toda_bn_stats
+    bn_finalize_kernel<<<ceil_div(c * 32, 128), 128, 0, (cudaStream_t)stream>>>(sums, 1, n, c, gamma, beta, eps, momentum,
+                                                                            running_mean, running_var, scale, shift, save_mean,
+                                                                            save_rstd);
     TODA_LAUNCH_OK();
     return TODA_OK;
 }

@@ -6,7 +6,8 @@
 #include "common.cuh"
 
 int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *w,
-                int cout, const float *bias, float *y, void *workspace, size_t workspace_bytes, cudaStream_t st);
+                int cout, const float *bias, float *y, double *bn_sums, void *workspace, size_t workspace_bytes,
+                cudaStream_t st);
 size_t conv_tc_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol);
 int conv_tc_wgrad(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
                   const float *dy, const void *dy_bf16, int cout, float *dw_param, void *workspace, size_t workspace_bytes,
@@ -248,6 +249,11 @@ extern "C" int toda_weight_repack(const float *w_param, int kvol, int cin, int c
     return TODA_OK;
 }
 
+// 1 when toda_spconv_fwd(precision) runs the tensor-core kernel for this shape (and can therefore fuse the BN statistics)
+extern "C" int toda_spconv_uses_tensor_cores(int cin, int cout, int kvol, int precision) {
+    return precision == TODA_CONV_BF16 && conv_tc_supported(cin, cout, kvol) ? 1 : 0;
+}
+
 extern "C" size_t toda_spconv_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol, int precision) {
     if (precision == TODA_CONV_BF16 && n_in >= 0 && cin > 0 && cout > 0 && kvol > 0 && conv_tc_supported(cin, cout, kvol))
         return conv_tc_fwd_workspace_bytes(n_in, cin, cout, kvol);
@@ -255,8 +261,8 @@ extern "C" size_t toda_spconv_fwd_workspace_bytes(int n_in, int cin, int cout, i
 }
 
 extern "C" int toda_spconv_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
-                               const float *w, int cout, const float *bias, float *y, int precision, void *workspace,
-                               size_t workspace_bytes, void *stream) {
+                               const float *w, int cout, const float *bias, float *y, double *bn_sums, int precision,
+                               void *workspace, size_t workspace_bytes, void *stream) {
     TODA_CHECK_ARG(n_in >= 0 && n_out >= 0 && cin > 0 && cout > 0 && kvol > 0, "spconv_fwd: bad sizes");
     if (n_out == 0) return TODA_OK;
     TODA_CHECK_ARG(x && nbr && w && y, "spconv_fwd: null pointer");
@@ -265,7 +271,8 @@ extern "C" int toda_spconv_fwd(const float *x, const void *x_bf16, int n_in, int
     // kernel selection by shape: the tensor-core kernel covers Cin in {<=16 (zero-padded to 16), 32, 64, 128} and
     // Cout in {16,32,64,128}; anything else (e.g. the dgrad of the 4/5-channel input layer) runs on the FFMA kernel.
     if (precision == TODA_CONV_BF16 && conv_tc_supported(cin, cout, kvol))
-        return conv_tc_fwd(x, x_bf16, n_in, cin, nbr, n_out, kvol, w, cout, bias, y, workspace, workspace_bytes, st);
+        return conv_tc_fwd(x, x_bf16, n_in, cin, nbr, n_out, kvol, w, cout, bias, y, bn_sums, workspace, workspace_bytes, st);
+    TODA_CHECK_ARG(!bn_sums, "spconv_fwd: fused BatchNorm statistics need the tensor-core kernel for this shape");
     if (cout <= 16) {
         dim3 grid(ceil_div(n_out, 256), ceil_div(cout, 16));
         conv_fwd_f32_kernel<256, 16><<<grid, kThreads, 0, st>>>(x, cin, nbr, n_out, kvol, w, cout, bias, y);

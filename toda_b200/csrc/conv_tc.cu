@@ -21,6 +21,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "epilogue.cuh"
 
 namespace {
 
@@ -165,7 +166,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
                                                                      const int *__restrict__ nbr, int n_out, int kvol,
                                                                      const __grid_constant__ CUtensorMap map_w /*[COUT][kvol*CIN] bf16*/,
                                                                      const float *__restrict__ bias, float *__restrict__ y,
-                                                                     int num_tiles, long long *__restrict__ dbg) {
+                                                                     double *__restrict__ bn_sums, int num_tiles,
+                                                                     long long *__restrict__ dbg) {
     static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 128, "UMMA N");
     static_assert(CIN == 16 || CIN == 32 || CIN == 64 || CIN == 128, "row = 32..256 bytes of bf16");
     using C = FwdCfg<COUT, KB>;
@@ -328,6 +330,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
     } else if (warp < 13) {
         // ------------------------------------------------------------------ epilogue (warps 9..12)
         const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+        float acc_s[COUT / 16], acc_q[COUT / 16];                // running per-channel sum / sum of squares (BatchNorm)
+#pragma unroll
+        for (int i = 0; i < COUT / 16; ++i) acc_s[i] = acc_q[i] = 0.f;
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int ab = it & 1;
@@ -344,21 +349,37 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
                       "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                     : "r"(taddr + n0));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + n0 + j) : 0.f);
                 if (row < n_out) {
                     float4 *dst = (float4 *)(y + (size_t)row * COUT + n0);
 #pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) {
-                        float4 o;
-                        o.x = __uint_as_float(v[4 * qq + 0]) + (bias ? __ldg(bias + n0 + 4 * qq + 0) : 0.f);
-                        o.y = __uint_as_float(v[4 * qq + 1]) + (bias ? __ldg(bias + n0 + 4 * qq + 1) : 0.f);
-                        o.z = __uint_as_float(v[4 * qq + 2]) + (bias ? __ldg(bias + n0 + 4 * qq + 2) : 0.f);
-                        o.w = __uint_as_float(v[4 * qq + 3]) + (bias ? __ldg(bias + n0 + 4 * qq + 3) : 0.f);
-                        dst[qq] = o;
+                    for (int qq = 0; qq < 4; ++qq) dst[qq] = make_float4(o[4 * qq], o[4 * qq + 1], o[4 * qq + 2], o[4 * qq + 3]);
+                }
+                if (bn_sums) {
+                    // statistics of the rows just produced, for the BatchNorm that follows: no second pass over y
+                    float sq[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        o[j] = row < n_out ? o[j] : 0.f;
+                        sq[j] = o[j] * o[j];
                     }
+                    acc_s[n0 / 16] += warp_colsum16(o, lane);
+                    acc_q[n0 / 16] += warp_colsum16(sq, lane);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(acc_empty + 8 * ab);
+        }
+        if (bn_sums && !(lane & 1)) {
+            // lane l (even) owns column n0 + ((l >> 1) & 15); one fp64 atomic per CTA-warp and channel
+            const int col = (lane >> 1) & 15;
+#pragma unroll
+            for (int i = 0; i < COUT / 16; ++i) {
+                atomicAdd(bn_sums + i * 16 + col, (double)acc_s[i]);
+                atomicAdd(bn_sums + COUT + i * 16 + col, (double)acc_q[i]);
+            }
         }
     } else {
         // ------------------------------------------------------------------ indexer (warp 13)
@@ -423,7 +444,7 @@ __global__ void weight_to_kmajor_bf16_kernel(const float *__restrict__ w, int kv
 static inline int pad16(int c) { return c < 16 ? 16 : c; }
 
 int conv_tma_fwd(const void *xb, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const void *wb, int cout,
-                 const float *bias, float *y, cudaStream_t st);
+                 const float *bias, float *y, double *bn_sums, cudaStream_t st);
 // 2-D bf16 row-major tensor map [rows][cols] with box [box_rows][box_cols], swizzle by box row bytes (conv_tma.cu)
 int conv_tma_make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols);
 
@@ -442,7 +463,8 @@ size_t conv_tc_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol) {
 }
 
 int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *w,
-                int cout, const float *bias, float *y, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+                int cout, const float *bias, float *y, double *bn_sums, void *workspace, size_t workspace_bytes,
+                cudaStream_t st) {
     size_t need = conv_tc_fwd_workspace_bytes(n_in, cin, cout, kvol);
     if (!workspace || workspace_bytes < need) {
         toda_set_error("spconv_fwd(bf16): workspace %zu < required %zu bytes", workspace_bytes, need);
@@ -466,6 +488,7 @@ int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int
     weight_to_kmajor_bf16_kernel<<<wave_grid((int64_t)kvol * cp * cout, 256), 256, 0, st>>>(w, kvol, cin, cp, cout, wb);
     TODA_LAUNCH_OK();
     cin = cp;
+    if (bn_sums) TODA_CUDA_OK(cudaMemsetAsync(bn_sums, 0, 2 * (size_t)cout * sizeof(double), st));
     // operand feed, chosen by shape from measurements on B200 (profiles/r01_feed_ab.md): TMA (gather4 rows + tiled
     // weights, conv_tma.cu) wins when rows are 256 bytes (Cin = Cout = 128); gather4 costs ~20-50 cycles per instruction
     // whatever the row width, so the cp.async producers below are faster for narrower rows.
@@ -473,7 +496,7 @@ int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int
     static int feed = -1;
     if (feed < 0) { const char *e = getenv("TODA_TC_FEED"); feed = !e ? 2 : (e[0] == 'c' ? 0 : 1); }
     if (feed == 1 || (feed == 2 && cin == 128 && cout == 128))
-        return conv_tma_fwd(xb, n_in, cin, nbr, n_out, kvol, wb, cout, bias, y, st);
+        return conv_tma_fwd(xb, n_in, cin, nbr, n_out, kvol, wb, cout, bias, y, bn_sums, st);
     int num_tiles = ceil_div(n_out, kTileM);
     int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;   // persistent: one CTA per SM walks the tiles
     CUtensorMap map_w;
@@ -482,8 +505,12 @@ int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int
     do {                                                                                                                     \
         constexpr int KB_ = (CO) <= 64 ? 2 : 1;                                                                              \
         constexpr int smem = FwdCfg<CO, KB_>::kSmem;                                                                         \
-        TODA_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_kernel<CI, CO, KB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        conv_tc_fwd_kernel<CI, CO, KB_><<<grid, kFwdThreads, smem, st>>>(xb, nbr, n_out, kvol, map_w, bias, y, num_tiles, g_dbg_timeline); \
+        static bool attr_set = false;                                                                                        \
+        if (!attr_set) {                                                                                                     \
+            TODA_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_kernel<CI, CO, KB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+            attr_set = true;                                                                                                 \
+        }                                                                                                                    \
+        conv_tc_fwd_kernel<CI, CO, KB_><<<grid, kFwdThreads, smem, st>>>(xb, nbr, n_out, kvol, map_w, bias, y, bn_sums, num_tiles, g_dbg_timeline); \
     } while (0)
 #define LAUNCH_TC_CO(CI)                                                                                 \
     switch (cout) {                                                                                      \
@@ -893,7 +920,11 @@ int conv_tc_wgrad(const float *x, const void *x_bf16, int n_in, int cin, const i
 #define LAUNCH_W(CI, NP, RW)                                                                                              \
     do {                                                                                                                   \
         constexpr int smem = WCfg<NP, RW>::kSmem;                                                                          \
-        TODA_CUDA_OK(cudaFuncSetAttribute(conv_tc_wgrad_kernel<CI, NP, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        static bool attr_set = false;                                                                                      \
+        if (!attr_set) {                                                                                                   \
+            TODA_CUDA_OK(cudaFuncSetAttribute(conv_tc_wgrad_kernel<CI, NP, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+            attr_set = true;                                                                                               \
+        }                                                                                                                  \
         conv_tc_wgrad_kernel<CI, NP, RW><<<grid, kWgradThreads, smem, st>>>(xb, nbr, n_out, kvol, dyb, cout, p.rows_per_split,  \
                                                                            p.passes_per_cta, partial);                      \
     } while (0)

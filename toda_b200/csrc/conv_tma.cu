@@ -14,6 +14,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "epilogue.cuh"
 
 namespace {
 
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_fwd_kernel(const __grid_
                                                                    const __grid_constant__ CUtensorMap map_w,
                                                                    const int *__restrict__ nbr, int n_in, int n_out, int kvol,
                                                                    const float *__restrict__ bias, float *__restrict__ y,
-                                                                   int num_tiles) {
+                                                                   double *__restrict__ bn_sums, int num_tiles) {
     using C = Cfg<CIN, COUT>;
     constexpr int S = C::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -241,13 +242,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_fwd_kernel(const __grid_
         }
     } else if (warp < kProdWarps + 5) {
         // ------------------------------------------------------------------ epilogue (4 warps)
-        const int q = warp & 3;
+        const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+        float acc_s[COUT / 16], acc_q[COUT / 16];                // running per-channel sum / sum of squares (BatchNorm)
+#pragma unroll
+        for (int i = 0; i < COUT / 16; ++i) acc_s[i] = acc_q[i] = 0.f;
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int ab = it & 1;
             mbar_wait(acc_full + 8 * ab, (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int row = t * kTileM + q * 32 + lane;
+            const int row = t * kTileM + q * 32 + lane;          // TMEM lane = tile row
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * COUT;
 #pragma unroll
             for (int n0 = 0; n0 < COUT; n0 += 16) {
@@ -258,21 +262,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_fwd_kernel(const __grid_
                       "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                     : "r"(taddr + n0));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + n0 + j) : 0.f);
                 if (row < n_out) {
                     float4 *dst = (float4 *)(y + (size_t)row * COUT + n0);
 #pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) {
-                        float4 o;
-                        o.x = __uint_as_float(v[4 * qq + 0]) + (bias ? __ldg(bias + n0 + 4 * qq + 0) : 0.f);
-                        o.y = __uint_as_float(v[4 * qq + 1]) + (bias ? __ldg(bias + n0 + 4 * qq + 1) : 0.f);
-                        o.z = __uint_as_float(v[4 * qq + 2]) + (bias ? __ldg(bias + n0 + 4 * qq + 2) : 0.f);
-                        o.w = __uint_as_float(v[4 * qq + 3]) + (bias ? __ldg(bias + n0 + 4 * qq + 3) : 0.f);
-                        dst[qq] = o;
+                    for (int qq = 0; qq < 4; ++qq) dst[qq] = make_float4(o[4 * qq], o[4 * qq + 1], o[4 * qq + 2], o[4 * qq + 3]);
+                }
+                if (bn_sums) {
+                    // statistics of the rows just produced, for the BatchNorm that follows: no second pass over y
+                    float sq[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        o[j] = row < n_out ? o[j] : 0.f;
+                        sq[j] = o[j] * o[j];
                     }
+                    acc_s[n0 / 16] += warp_colsum16(o, lane);
+                    acc_q[n0 / 16] += warp_colsum16(sq, lane);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(acc_empty + 8 * ab);
+        }
+        if (bn_sums && !(lane & 1)) {
+            // lane l (even) owns column n0 + ((l >> 1) & 15); one fp64 atomic per CTA-warp and channel
+            const int col = (lane >> 1) & 15;
+#pragma unroll
+            for (int i = 0; i < COUT / 16; ++i) {
+                atomicAdd(bn_sums + i * 16 + col, (double)acc_s[i]);
+                atomicAdd(bn_sums + COUT + i * 16 + col, (double)acc_q[i]);
+            }
         }
     } else {
         // ------------------------------------------------------------------ indexer
@@ -333,15 +353,19 @@ int make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint
 
 template <int CIN, int COUT>
 int launch(const __nv_bfloat16 *xb, int n_in, const int32_t *nbr, int n_out, int kvol, const __nv_bfloat16 *wb, const float *bias,
-           float *y, cudaStream_t st) {
+           float *y, double *bn_sums, cudaStream_t st) {
     using C = Cfg<CIN, COUT>;
     CUtensorMap mx, mw;
     if (int rc = make_map(&mx, xb, (uint64_t)n_in, CIN, 1, C::kRowElems)) return rc;              // gather4: box = one row
     if (int rc = make_map(&mw, wb, COUT, (uint64_t)kvol * CIN, COUT, C::kRowElems)) return rc;
     int num_tiles = ceil_div(n_out, kTileM);
     int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
-    TODA_CUDA_OK(cudaFuncSetAttribute(conv_tma_fwd_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
-    conv_tma_fwd_kernel<CIN, COUT><<<grid, kThreads, C::kSmem, st>>>(mx, mw, nbr, n_in, n_out, kvol, bias, y, num_tiles);
+    static bool attr_set = false;      // per <CIN, COUT> instantiation
+    if (!attr_set) {
+        TODA_CUDA_OK(cudaFuncSetAttribute(conv_tma_fwd_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+        attr_set = true;
+    }
+    conv_tma_fwd_kernel<CIN, COUT><<<grid, kThreads, C::kSmem, st>>>(mx, mw, nbr, n_in, n_out, kvol, bias, y, bn_sums, num_tiles);
     TODA_LAUNCH_OK();
     return TODA_OK;
 }
@@ -354,14 +378,14 @@ int conv_tma_make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t c
 
 // xb: bf16 [n_in][cin], wb: bf16 [cout][kvol*cin]; cin, cout in {16,32,64,128}
 int conv_tma_fwd(const void *xb, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const void *wb, int cout,
-                 const float *bias, float *y, cudaStream_t st) {
+                 const float *bias, float *y, double *bn_sums, cudaStream_t st) {
     const __nv_bfloat16 *x = (const __nv_bfloat16 *)xb, *w = (const __nv_bfloat16 *)wb;
 #define CASE_CO(CI)                                                                                    \
     switch (cout) {                                                                                    \
-        case 16: return launch<CI, 16>(x, n_in, nbr, n_out, kvol, w, bias, y, st);                     \
-        case 32: return launch<CI, 32>(x, n_in, nbr, n_out, kvol, w, bias, y, st);                     \
-        case 64: return launch<CI, 64>(x, n_in, nbr, n_out, kvol, w, bias, y, st);                     \
-        case 128: return launch<CI, 128>(x, n_in, nbr, n_out, kvol, w, bias, y, st);                   \
+        case 16: return launch<CI, 16>(x, n_in, nbr, n_out, kvol, w, bias, y, bn_sums, st);                     \
+        case 32: return launch<CI, 32>(x, n_in, nbr, n_out, kvol, w, bias, y, bn_sums, st);                     \
+        case 64: return launch<CI, 64>(x, n_in, nbr, n_out, kvol, w, bias, y, bn_sums, st);                     \
+        case 128: return launch<CI, 128>(x, n_in, nbr, n_out, kvol, w, bias, y, bn_sums, st);                   \
     }                                                                                                  \
     break;
     switch (cin) {

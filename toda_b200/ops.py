@@ -52,22 +52,36 @@ def profile_end():
     return [dict(name=n, ms=a.elapsed_time(b), **m) for (n, m, a, b) in rec]
 
 
-class _timed:
-    def __init__(self, name, **meta):
+class _Timed:
+    def __init__(self, name, meta):
         self.name, self.meta = name, meta
 
     def __enter__(self):
-        if _prof is not None:
-            self.a = torch.cuda.Event(enable_timing=True)
-            self.a.record()
+        self.a = torch.cuda.Event(enable_timing=True)
+        self.a.record()
         return self
 
     def __exit__(self, *exc):
-        if _prof is not None:
-            b = torch.cuda.Event(enable_timing=True)
-            b.record()
-            _prof.append((self.name, self.meta, self.a, b))
+        b = torch.cuda.Event(enable_timing=True)
+        b.record()
+        _prof.append((self.name, self.meta, self.a, b))
         return False
+
+
+class _NoTimer:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_TIMER = _NoTimer()
+
+
+def _timed(name, **meta):
+    """Context manager around one C-ABI call: records CUDA events only while a profile pass is active."""
+    return _Timed(name, meta) if _prof is not None else _NO_TIMER
 
 
 def _stream():
@@ -385,21 +399,22 @@ def _bf16_shadow_of(t):
     return None
 
 
-def _conv_call(x, xb, cin, nbr, n_out, kvol, w, cout, bias, precision, what="conv_fwd", rb=None):
+def _conv_call(x, xb, cin, nbr, n_out, kvol, w, cout, bias, precision, what="conv_fwd", rb=None, bn_sums=None):
     y = torch.empty((n_out, cout), dtype=torch.float32, device=x.device)
     L = _C.lib()
     ws_bytes = L.toda_spconv_fwd_workspace_bytes(x.shape[0], cin, cout, kvol, precision)
     ws = _workspace("conv", ws_bytes, x.device) if ws_bytes else None
     with _timed(what, n_in=x.shape[0], n_out=n_out, cin=cin, cout=cout, kvol=kvol, precision=precision, rb=id(rb)):
         _C.check(L.toda_spconv_fwd(_p(x), _p(xb), x.shape[0], cin, _p(nbr), n_out, kvol, _p(w), cout, _p(bias), _p(y),
-                                   precision, _p(ws), ws.numel() if ws is not None else 0, _stream()), "toda_spconv_fwd")
+                                   _p(bn_sums), precision, _p(ws), ws.numel() if ws is not None else 0, _stream()),
+                 "toda_spconv_fwd")
     _count(1)
     return y
 
 
 class _SparseConv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, x_bf16, weight, bias, rb: Rulebook, precision):
+    def forward(ctx, x, x_bf16, weight, bias, rb: Rulebook, precision, want_stats):
         x = _need(x.contiguous(), torch.float32, "features")
         weight = _need(weight.contiguous(), torch.float32, "weight")
         cout, cin = weight.shape[0], weight.shape[4]
@@ -409,13 +424,18 @@ class _SparseConv(torch.autograd.Function):
             x_bf16 = None
         w = _repack(weight, False, False)
         b = bias.contiguous() if bias is not None else None
-        y = _conv_call(x, x_bf16, cin, rb.nbr_fwd, rb.n_out, rb.kvol, w, cout, b, precision, "conv_fwd", rb)
+        sums = None
+        if want_stats and rb.n_out > 0 and _C.lib().toda_spconv_uses_tensor_cores(cin, cout, rb.kvol, precision):
+            sums = torch.empty((2 * cout,), dtype=torch.float64, device=x.device)
+        y = _conv_call(x, x_bf16, cin, rb.nbr_fwd, rb.n_out, rb.kvol, w, cout, b, precision, "conv_fwd", rb, sums)
         ctx.save_for_backward(x, weight, x_bf16)
         ctx.rb, ctx.precision, ctx.has_bias = rb, precision, bias is not None
-        return y
+        if sums is not None:
+            ctx.mark_non_differentiable(sums)
+        return y, sums
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dsums=None):
         x, weight, xb = ctx.saved_tensors
         rb, precision = ctx.rb, ctx.precision
         cout, cin = weight.shape[0], weight.shape[4]
@@ -439,11 +459,14 @@ class _SparseConv(torch.autograd.Function):
             _count(2)
         if ctx.has_bias and ctx.needs_input_grad[3]:
             db = col_sum(dy)
-        return dx, None, dw, db, None, None
+        return dx, None, dw, db, None, None, None
 
 
-def sparse_conv(x, weight, bias, rb, precision=CONV_FP32, x_bf16=None):
-    return _SparseConv.apply(x, x_bf16, weight, bias, rb, precision)
+def sparse_conv(x, weight, bias, rb, precision=CONV_FP32, x_bf16=None, want_stats=False):
+    """y = conv(x).  want_stats: also return the per-channel (sum, sum of squares) of y accumulated by the kernel's
+    epilogue (double[2*Cout], or None when this shape does not run on the tensor-core kernel) for bn_act(sums=...)."""
+    y, sums = _SparseConv.apply(x, x_bf16, weight, bias, rb, precision, want_stats)
+    return (y, sums) if want_stats else y
 
 
 def col_sum(t):
@@ -461,7 +484,7 @@ def col_sum(t):
 # ------------------------------------------------------------------------------------------------
 class _BNAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, y, gamma, beta, running_mean, running_var, eps, momentum, training, residual, relu, want_bf16):
+    def forward(ctx, y, gamma, beta, running_mean, running_var, eps, momentum, training, residual, relu, want_bf16, sums):
         y = _need(y.contiguous(), torch.float32, "bn input")
         n, c = y.shape
         dev = y.device
@@ -469,7 +492,14 @@ class _BNAct(torch.autograd.Function):
         scale = torch.empty((c,), dtype=torch.float32, device=dev)
         shift = torch.empty_like(scale)
         ws = _workspace("bn", L.toda_bn_workspace_bytes(c), dev)
-        if training:
+        if training and sums is not None:
+            mean = torch.empty_like(scale)
+            rstd = torch.empty_like(scale)
+            _C.check(L.toda_bn_finalize_sums(_p(sums), n, c, _p(gamma), _p(beta), float(eps), float(momentum),
+                                             _p(running_mean), _p(running_var), _p(scale), _p(shift), _p(mean), _p(rstd),
+                                             _stream()), "toda_bn_finalize_sums")
+            _count(1)
+        elif training:
             mean = torch.empty_like(scale)
             rstd = torch.empty_like(scale)
             with _timed("bn_stats", n=n, c=c):
@@ -516,17 +546,18 @@ class _BNAct(torch.autograd.Function):
         _count(3)
         if dyb is not None:
             dy._toda_bf16 = (dyb, dy._version)     # picked up by the producing conv's backward (see _bf16_shadow_of)
-        return dy, dgamma, dbeta, None, None, None, None, None, dres, None, None
+        return dy, dgamma, dbeta, None, None, None, None, None, dres, None, None, None
 
 
-def bn_act(y, bn: torch.nn.BatchNorm1d, residual=None, relu=True, want_bf16=False):
+def bn_act(y, bn: torch.nn.BatchNorm1d, residual=None, relu=True, want_bf16=False, sums=None):
     """BatchNorm1d (+ residual) (+ ReLU) with the module's parameters / running stats
-    (spconv_backbone.py L23-24, L54-64).  want_bf16: also return the bf16 copy written by the same pass."""
+    (spconv_backbone.py L23-24, L54-64).  want_bf16: also return the bf16 copy written by the same pass.
+    sums: per-channel (sum, sum of squares) of y from the producing convolution's epilogue (skips the statistics pass)."""
     training = bn.training or bn.running_mean is None
     if training and bn.running_mean is not None and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
     a, ab = _BNAct.apply(y, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, training, residual,
-                         relu, want_bf16)
+                         relu, want_bf16, sums if training else None)
     return (a, ab) if want_bf16 else a
 
 

@@ -41,7 +41,7 @@ def _triple(v):
 
 class SparseConvTensor:
     def __init__(self, features, indices, spatial_shape, batch_size, grid=None, voxel_num=None, indice_dict=None,
-                 benchmark=False, _index=None, _features_bf16=None):
+                 benchmark=False, _index=None, _features_bf16=None, _bn_sums=None):
         self.features = features
         self.indices = indices
         self.spatial_shape = [int(s) for s in spatial_shape]
@@ -52,6 +52,7 @@ class SparseConvTensor:
         self.benchmark = benchmark
         self._index = _index          # ops.OccupancyIndex when rows are in canonical order
         self._features_bf16 = _features_bf16   # bf16 copy of `features` written by the fused BN pass (tensor-core operand)
+        self._bn_sums = _bn_sums               # per-channel (sum, sum^2) of `features` from the conv epilogue, for the next BN
 
     def replace_feature(self, feature, _features_bf16=None):
         return SparseConvTensor(feature, self.indices, self.spatial_shape, self.batch_size, self.grid, self.voxel_num,
@@ -100,7 +101,7 @@ def bn_act_tensor(x, bn, residual, relu):
     """Fused BatchNorm1d (+residual) (+ReLU) on a SparseConvTensor; in bf16 mode the same pass also writes the bf16
     copy that the next convolution gathers from."""
     if _precision == ops.CONV_BF16:
-        a, ab = ops.bn_act(x.features, bn, residual, relu, want_bf16=True)
+        a, ab = ops.bn_act(x.features, bn, residual, relu, want_bf16=True, sums=x._bn_sums)
         return x.replace_feature(a, ab)
     return x.replace_feature(ops.bn_act(x.features, bn, residual, relu))
 
@@ -215,9 +216,14 @@ class SparseConvolution(SparseModule):
         assert isinstance(x, SparseConvTensor)
         x = x.canonical()
         rb, index_out = self._rulebook(x)
-        y = ops.sparse_conv(x.features, self.weight, self.bias, rb, _precision, x._features_bf16)
+        # in tensor-core mode the epilogue also accumulates the statistics a following BatchNorm needs (train mode)
+        want_stats = _precision == ops.CONV_BF16 and self.training and torch.is_grad_enabled()
+        if want_stats:
+            y, sums = ops.sparse_conv(x.features, self.weight, self.bias, rb, _precision, x._features_bf16, want_stats=True)
+        else:
+            y, sums = ops.sparse_conv(x.features, self.weight, self.bias, rb, _precision, x._features_bf16), None
         return SparseConvTensor(y, rb.out_coords, rb.out_shape, x.batch_size, x.grid, x.voxel_num, x.indice_dict,
-                                x.benchmark, index_out)
+                                x.benchmark, index_out, None, sums)
 
 
 class SubMConv3d(SparseConvolution):
