@@ -6,7 +6,7 @@ import numpy as np, torch
 from toda_b200 import ops, _C
 from tests import parity_utils as PU
 cin, cout, n = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
-shape, batch = [21, 400, 400], 2
+shape, batch = ([int(v) for v in sys.argv[4].split(",")] if len(sys.argv) > 4 else [21, 400, 400]), 2
 feats, idx = PU.random_sparse(3, batch, shape, n, cin)
 x = torch.from_numpy(feats).cuda()
 index = ops.OccupancyIndex(batch, shape, torch.device("cuda", 0), "dbg")
@@ -28,3 +28,7 @@ print("conv %d->%d n=%d: %.3f ms (incl. pre-passes)" % (cin, cout, n, e0.elapsed
 print("chunk " + " ".join("%12s" % s for s in names))
 for g in range(8, 40):
     print("%5d " % g + " ".join("%12d" % (t[r, g] - t0) for r in range(7)))
+sig = t[3, 8:250]
+print("producer chunk period (cycles): median %d  mean %d;  MMA wait (full ok - wait full) median %d  mean %d;  pairs/row %.2f" % (
+    np.median(np.diff(sig)), np.mean(np.diff(sig)), np.median(t[5, 8:250] - t[4, 8:250]), np.mean(t[5, 8:250] - t[4, 8:250]),
+    float((rb.nbr_fwd >= 0).sum().item()) / n))

@@ -822,26 +822,30 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_tc_wgrad_kernel(const _
 }
 
 // fixed-order reduction over splits into the parameter layout (Cout, kvol, Cin)
-__global__ void wgrad_tc_reduce_kernel(const float *__restrict__ partial, int splits, int kvol, int cin, int cpad, int cout,
-                                       float *__restrict__ dw_param) {
-    // 8 lanes per output element, each summing every 8th split; combined with a fixed shuffle tree (deterministic)
-    size_t per = (size_t)kvol * cin * cout, per_pad = (size_t)kvol * cpad * cout;
-    const int sub = threadIdx.x & 7;
-    for (size_t e = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 3; e < ((per + 31) & ~(size_t)31);
-         e += ((size_t)gridDim.x * blockDim.x) >> 3) {
+// partial: [splits][kvol][cpad][cout].  Block = 32 consecutive source elements (coalesced 128-byte reads) x 8 split
+// subsets, combined through shared memory in a fixed tree (deterministic); the transposing write is the small side.
+__global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float *__restrict__ partial, int splits, int kvol, int cin,
+                                                              int cpad, int cout, float *__restrict__ dw_param) {
+    __shared__ float red[8][33];
+    const size_t per_pad = (size_t)kvol * cpad * cout;
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    for (size_t e0 = (size_t)blockIdx.x * 32; e0 < per_pad; e0 += (size_t)gridDim.x * 32) {
+        const size_t e = e0 + x;
         float s = 0.f;
-        if (e < per) {
-            int ci = (int)(e % cin);
-            size_t t = e / cin;
-            int k = (int)(t % kvol);
-            int co = (int)(t / kvol);
-            size_t src = ((size_t)k * cpad + ci) * cout + co;
-            for (int sp = sub; sp < splits; sp += 8) s += partial[sp * per_pad + src];
+        if (e < per_pad) {
+#pragma unroll 4
+            for (int sp = y; sp < splits; sp += 8) s += __ldg(partial + sp * per_pad + e);
         }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        if (e < per && sub == 0) dw_param[e] = s;
+        red[y][x] = s;
+        __syncthreads();
+        if (y == 0 && e < per_pad) {
+            s = ((red[0][x] + red[1][x]) + (red[2][x] + red[3][x])) + ((red[4][x] + red[5][x]) + (red[6][x] + red[7][x]));
+            const int co = (int)(e % cout);
+            const size_t t = e / cout;
+            const int ci = (int)(t % cpad), k = (int)(t / cpad);
+            if (ci < cin) dw_param[((size_t)co * kvol + k) * cin + ci] = s;
+        }
+        __syncthreads();
     }
 }
 
@@ -938,8 +942,8 @@ int conv_tc_wgrad(const float *x, const void *x_bf16, int n_in, int cin, const i
     }
 #undef LAUNCH_W
     TODA_LAUNCH_OK();
-    size_t per = (size_t)kvol * cin_real * cout;
-    wgrad_tc_reduce_kernel<<<wave_grid(per * 8, 256), 256, 0, st>>>(partial, p.splits, kvol, cin_real, cin, cout, dw_param);
+    size_t per_pad = (size_t)kvol * cin * cout;
+    wgrad_tc_reduce_kernel<<<wave_grid(per_pad * 8, 256), 256, 0, st>>>(partial, p.splits, kvol, cin_real, cin, cout, dw_param);
     TODA_LAUNCH_OK();
     return TODA_OK;
 }

@@ -227,6 +227,7 @@ class OccupancyIndex:
         self.key = (("index", tag, self.batch, d, h, w), device.index)
         self.buf = _workspace(self.key[0], nbytes, device, zero=True)
         self.coords = None
+        self.frame_counts = None
         self.n = 0
         self._marked = False   # True while extra marks (not described by self.coords) may be in the buffer
 
@@ -429,6 +430,7 @@ class _SparseConv(torch.autograd.Function):
             sums = torch.empty((2 * cout,), dtype=torch.float64, device=x.device)
         y = _conv_call(x, x_bf16, cin, rb.nbr_fwd, rb.n_out, rb.kvol, w, cout, b, precision, "conv_fwd", rb, sums)
         ctx.save_for_backward(x, weight, x_bf16)
+        ctx.set_materialize_grads(False)      # no zero tensors for the non-differentiable outputs
         ctx.rb, ctx.precision, ctx.has_bias = rb, precision, bias is not None
         if sums is not None:
             ctx.mark_non_differentiable(sums)
@@ -436,6 +438,8 @@ class _SparseConv(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, _dsums=None):
+        if dy is None:
+            return (None,) * 7
         x, weight, xb = ctx.saved_tensors
         rb, precision = ctx.rb, ctx.precision
         cout, cin = weight.shape[0], weight.shape[4]
@@ -521,6 +525,7 @@ class _BNAct(torch.autograd.Function):
                      "toda_bn_apply")
         _count(1)
         ctx.save_for_backward(y, a, gamma, mean, rstd)
+        ctx.set_materialize_grads(False)      # the bf16 copy is non-differentiable: no zero tensor for it in backward
         ctx.cfg = (bool(training), bool(relu), residual is not None, bool(want_bf16))
         if ab is not None:
             ctx.mark_non_differentiable(ab)
@@ -528,6 +533,8 @@ class _BNAct(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, da, _dab=None):
+        if da is None:
+            return (None,) * 12
         y, a, gamma, mean, rstd = ctx.saved_tensors
         training, relu, has_res, want_bf16 = ctx.cfg
         n, c = y.shape

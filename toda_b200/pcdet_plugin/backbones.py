@@ -104,12 +104,24 @@ def make_backbones(sp, bn_act):
             self.num_point_features = cout
             self.backbone_channels = dict(st["channels"])
 
+        def plan_geometry(self, voxel_coords, batch_size, canonical=False):
+            """Coordinate-only part of forward(): the index and every rulebook, as a plan that forward() picks up from
+            batch_dict['spconv_geometry'] (toda_b200.pipeline builds it one batch ahead on a side stream)."""
+            convs = [m for m in self.modules() if isinstance(m, sp.SparseConvolution)]     # registration = execution order
+            return sp.plan_geometry(convs, voxel_coords, self.sparse_shape, batch_size, assume_canonical=canonical)
+
         def forward(self, batch_dict):
             voxel_features, voxel_coords = batch_dict["voxel_features"], batch_dict["voxel_coords"]
-            x = sp.SparseConvTensor(features=voxel_features, indices=voxel_coords.int(), spatial_shape=self.sparse_shape,
-                                    batch_size=batch_dict["batch_size"])
-            if batch_dict.get("voxel_coords_canonical", False) and hasattr(x, "canonical"):
-                x = x.canonical(assume_canonical=True)
+            plan = batch_dict.get("spconv_geometry")
+            if plan is not None:
+                if plan.coords.shape[0] != voxel_features.shape[0]:
+                    raise ValueError("spconv_geometry was planned for a different batch")
+                x = plan.sparse_tensor(voxel_features)
+            else:
+                x = sp.SparseConvTensor(features=voxel_features, indices=voxel_coords.int(), spatial_shape=self.sparse_shape,
+                                        batch_size=batch_dict["batch_size"])
+                if batch_dict.get("voxel_coords_canonical", False) and hasattr(x, "canonical"):
+                    x = x.canonical(assume_canonical=True)
             x = self.conv_input(x)
             x_conv1 = self.conv1(x)
             x_conv2 = self.conv2(x_conv1)

@@ -226,6 +226,72 @@ class SparseConvolution(SparseModule):
                                 x.benchmark, index_out, None, sums)
 
 
+class GeometryPlan:
+    """Everything about a sparse tensor chain that depends on coordinates only: the canonical input index and the
+    rulebook of every `indice_key`.  Built ahead of time (e.g. on a side stream while the previous batch trains, see
+    toda_b200.pipeline) it makes the forward pass free of index kernels and host synchronisation."""
+
+    def __init__(self, index, coords, spatial_shape, batch_size, indice_dict):
+        self.index, self.coords, self.spatial_shape, self.batch_size = index, coords, spatial_shape, batch_size
+        self.indice_dict = indice_dict
+
+    def tensors(self):
+        out = [self.coords, self.index.frame_counts]
+        for rb, index_out in self.indice_dict.values():
+            out += [rb.out_coords, rb.nbr_fwd]
+            if rb.nbr_bwd is not None:
+                out.append(rb.nbr_bwd)
+            if index_out.frame_counts is not None:
+                out.append(index_out.frame_counts)
+        return [t for t in out if t is not None]
+
+    def sparse_tensor(self, features, features_bf16=None):
+        return SparseConvTensor(features, self.coords, self.spatial_shape, self.batch_size, indice_dict=self.indice_dict,
+                                _index=self.index, _features_bf16=features_bf16)
+
+
+class _GeometryCursor:
+    """Stand-in for a SparseConvTensor while planning: coordinates and index, no features."""
+
+    class _Rows:
+        def __init__(self, n):
+            self.shape = (n,)
+
+    def __init__(self, index, coords, spatial_shape, indice_dict):
+        self._index, self.indices, self.spatial_shape, self.indice_dict = index, coords, spatial_shape, indice_dict
+        self.features = self._Rows(coords.shape[0])
+
+
+def plan_geometry(convs, indices, spatial_shape, batch_size, assume_canonical=False):
+    """Rulebooks for `convs` (SparseConvolution modules in execution order) applied as a chain to a tensor with
+    `indices` (N,4) [b,z,y,x].  Needs canonical (b,z,y,x) row order (what toda_b200's voxelizer emits in canonical
+    mode): a plan cannot permute features it has not seen."""
+    x = SparseConvTensor(None, indices, spatial_shape, batch_size)
+    if not assume_canonical:
+        idx = indices.int().contiguous()
+        index = ops.OccupancyIndex(batch_size, x.spatial_shape, idx.device, "level")
+        index.insert(idx)
+        coords = index.build(idx.shape[0])
+        if index.n != idx.shape[0] or not bool(torch.equal(coords, idx)):
+            raise ValueError("plan_geometry needs unique coordinates in canonical (b,z,y,x) order")
+    else:
+        idx = indices if indices.dtype == torch.int32 else indices.int()
+        idx = idx.contiguous()
+        index = ops.OccupancyIndex(batch_size, x.spatial_shape, idx.device, "level")
+        index.insert(idx)
+        coords = index.build(idx.shape[0], known_n=idx.shape[0])
+    indice_dict = {}
+    plan = GeometryPlan(index, coords, x.spatial_shape, x.batch_size, indice_dict)
+    cur = _GeometryCursor(index, coords, x.spatial_shape, indice_dict)
+    for m in convs:
+        if m.indice_key is None:
+            raise ValueError("plan_geometry needs an indice_key on every convolution")
+        rb, index_out = m._rulebook(cur)
+        if not m.subm:
+            cur = _GeometryCursor(index_out, rb.out_coords, rb.out_shape, indice_dict)
+    return plan
+
+
 class SubMConv3d(SparseConvolution):
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
                  indice_key=None, algo=None, fp32_accum=None, name=None):
