@@ -226,9 +226,13 @@ def run_ours(args, rank, world, local_rank):
 
     def front(points, offsets, pending):
         t0 = time.perf_counter()
+        if trace is not None:
+            import faulthandler
+            faulthandler.dump_traceback_later(0.012, file=sys.stderr)     # where is the host if a front stalls?
         h = pipe.submit({"points": points, "point_frame_offsets": offsets, "batch_size": FRAMES_PER_GPU},
                         inputs_pending=pending)
         if trace is not None:
+            faulthandler.cancel_dump_traceback_later()
             trace.append(("front", round((time.perf_counter() - t0) * 1e3, 2)))
         return h
 

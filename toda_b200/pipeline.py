@@ -17,6 +17,8 @@ pcdet/datasets/processor/data_processor.py L115-143 under torch DataLoader prefe
         loss = head(backbone(batch_dict)) ...      # launches only
         nxt = pipe.submit(next_batch)              # overlaps with the kernels queued above
 """
+from collections import deque
+
 import torch
 
 
@@ -31,6 +33,7 @@ class InputPipeline:
         self.device = torch.device(device)
         lo, hi = torch.cuda.Stream.priority_range()      # (lowest, highest): highest is the numerically smaller one
         self.stream = torch.cuda.Stream(self.device, priority=hi)
+        self._started = deque()     # main-stream events, one per consume(): "the batch before this one has finished"
         if reserve_bytes:
             # the caching allocator keeps one pool per stream: give the side stream its blocks up front so that row
             # counts that differ from batch to batch never reach cudaMalloc (which synchronises the device)
@@ -43,6 +46,15 @@ class InputPipeline:
         pinned host tensors (copied here, asynchronously) or device tensors.  inputs_pending: device inputs may still
         be being written by work queued on the current stream, so the side stream waits for it; pass False for inputs
         that are already complete (then the front starts at once, next to whatever the main stream is running)."""
+        # Bound the run-ahead: the front has no dependency on the main stream, so without this the host (throttled only
+        # by the front's own small syncs) queues several steps ahead of the GPU, every queued batch keeps its ~0.5 GB of
+        # tables alive, the side pool runs dry and torch falls back to cudaMalloc, which stalls for as long as the queue
+        # in front of it (measured: 20-90 ms).  Waiting for the start of the batch consumed last keeps one full batch
+        # queued on the main stream (the GPU never idles) and at most three batches' tables alive.
+        while len(self._started) > 1:
+            self._started.popleft()
+        if self._started:
+            self._started[0].synchronize()
         if inputs_pending and any(torch.is_tensor(v) and v.is_cuda for v in batch_dict.values()):
             self.stream.wait_stream(torch.cuda.current_stream(self.device))
         bd = dict(batch_dict)
@@ -68,6 +80,9 @@ class InputPipeline:
     def consume(self, handle):
         """Makes the current stream wait for the front of that batch and hands over its batch_dict."""
         main = torch.cuda.current_stream(self.device)
+        started = torch.cuda.Event()
+        started.record(main)           # completes when everything queued before this batch (the previous batch) is done
+        self._started.append(started)
         main.wait_event(handle.ready)
         for t in handle.tensors:
             t.record_stream(main)      # allocated on the side stream's pool, read by main-stream kernels from now on
