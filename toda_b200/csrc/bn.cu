@@ -122,12 +122,24 @@ static void launch_col_reduce(const float *p0, const float *p1, const float *p2,
         col_reduce_kernel<MODE><<<kPartials, kThreads, 0, st>>>(p0, p1, p2, n, c, mean, rstd, relu, partial);
 }
 
-// fixed-order sum of the per-CTA partials of one channel: one warp per channel, lanes stride over the partials
+// fixed-order sum of the per-CTA partials of one channel: one warp per channel, lanes stride over the partials.
+// All loads of a lane are issued before the first add (the loop used to be a chain of ~10 dependent L2 round trips,
+// which made this tiny kernel take as long as a third of the streaming pass next to it).
 __device__ __forceinline__ void warp_sum_partials(const double *__restrict__ partial, int nblocks, int c, int ch, double &s,
                                                   double &ss) {
     const int lane = threadIdx.x & 31;
+    constexpr int kPerLane = (kPartials + 31) / 32;
+    double va[kPerLane], vb[kPerLane];
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+        const int j = lane + 32 * i;
+        const bool ok = j < nblocks;
+        va[i] = ok ? partial[((size_t)j * 2) * c + ch] : 0.0;
+        vb[i] = ok ? partial[((size_t)j * 2 + 1) * c + ch] : 0.0;
+    }
     double a = 0.0, b = 0.0;
-    for (int j = lane; j < nblocks; j += 32) { a += partial[((size_t)j * 2) * c + ch]; b += partial[((size_t)j * 2 + 1) * c + ch]; }
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) { a += va[i]; b += vb[i]; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
     s = a; ss = b;
@@ -339,6 +351,17 @@ extern "C" int toda_bn_eval_coeffs(const float *gamma, const float *beta, const 
     return TODA_OK;
 }
 
+// Grid of a grid-stride streaming kernel: exactly the CTAs that are resident at once (occupancy x SMs), never more than
+// the work.  A grid that is 1.3-1.6 waves (what a fixed 8 CTAs/SM gave for the 34- and 41-register kernels) leaves most
+// SMs idle during the second, partial wave.
+template <typename K> static int resident_grid(K kernel, int64_t items) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    int64_t need = (items + kThreads - 1) / kThreads;
+    int64_t cap = (int64_t)per_sm * kNumSMs;
+    return (int)(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
 extern "C" int toda_bn_apply(const float *y, int n, int c, const float *scale, const float *shift, const float *residual,
                              int relu, float *a, void *a_bf16, void *stream) {
     TODA_CHECK_ARG(n >= 0 && c > 0, "bn_apply: bad sizes");
@@ -346,10 +369,19 @@ extern "C" int toda_bn_apply(const float *y, int n, int c, const float *scale, c
     TODA_CHECK_ARG(y && scale && shift && a, "bn_apply: null pointer");
     long long total = (long long)n * c;
     cudaStream_t st = (cudaStream_t)stream;
+    static int per_sm_vec = 0, per_sm_scalar = 0;     // resident CTAs per SM of the two variants (queried once)
+    if (!per_sm_vec) {
+        per_sm_vec = resident_grid(bn_apply_kernel<true>, (int64_t)1 << 40) / kNumSMs;
+        per_sm_scalar = resident_grid(bn_apply_kernel<false>, (int64_t)1 << 40) / kNumSMs;
+    }
+    auto grid_for = [](int64_t items, int per_sm) {
+        int64_t need = (items + kThreads - 1) / kThreads, cap = (int64_t)per_sm * kNumSMs;
+        return (int)(need < 1 ? 1 : (need < cap ? need : cap));
+    };
     if (c % 4 == 0)
-        bn_apply_kernel<true><<<wave_grid(total / 4, kThreads), kThreads, 0, st>>>(y, total, c, scale, shift, residual, relu, a, (__nv_bfloat16 *)a_bf16);
+        bn_apply_kernel<true><<<grid_for(total / 4, per_sm_vec), kThreads, 0, st>>>(y, total, c, scale, shift, residual, relu, a, (__nv_bfloat16 *)a_bf16);
     else
-        bn_apply_kernel<false><<<wave_grid(total, kThreads), kThreads, 0, st>>>(y, total, c, scale, shift, residual, relu, a, (__nv_bfloat16 *)a_bf16);
+        bn_apply_kernel<false><<<grid_for(total, per_sm_scalar), kThreads, 0, st>>>(y, total, c, scale, shift, residual, relu, a, (__nv_bfloat16 *)a_bf16);
     TODA_LAUNCH_OK();
     return TODA_OK;
 }
@@ -370,11 +402,20 @@ extern "C" int toda_bn_bwd(const float *da, const float *a, const float *y, int 
     TODA_LAUNCH_OK();
     if (n > 0) {
         long long total = (long long)n * c;
+        static int per_sm_vec = 0, per_sm_scalar = 0;
+        if (!per_sm_vec) {
+            per_sm_vec = resident_grid(bn_bwd_apply_kernel<true>, (int64_t)1 << 40) / kNumSMs;
+            per_sm_scalar = resident_grid(bn_bwd_apply_kernel<false>, (int64_t)1 << 40) / kNumSMs;
+        }
+        auto grid_for = [](int64_t items, int per_sm) {
+            int64_t need = (items + kThreads - 1) / kThreads, cap = (int64_t)per_sm * kNumSMs;
+            return (int)(need < 1 ? 1 : (need < cap ? need : cap));
+        };
         if (c % 4 == 0 && kThreads % (c / 4) == 0)   // grid*block is then a multiple of c/4: a thread keeps its 4 channels
-            bn_bwd_apply_kernel<true><<<wave_grid(total / 4, kThreads), kThreads, 0, st>>>(
+            bn_bwd_apply_kernel<true><<<grid_for(total / 4, per_sm_vec), kThreads, 0, st>>>(
                 da, a, y, total, c, n, gamma, save_mean, save_rstd, sums, relu, training, dy, dresidual, (__nv_bfloat16 *)dy_bf16);
         else
-            bn_bwd_apply_kernel<false><<<wave_grid(total, kThreads), kThreads, 0, st>>>(
+            bn_bwd_apply_kernel<false><<<grid_for(total, per_sm_scalar), kThreads, 0, st>>>(
                 da, a, y, total, c, n, gamma, save_mean, save_rstd, sums, relu, training, dy, dresidual, (__nv_bfloat16 *)dy_bf16);
         TODA_LAUNCH_OK();
     }
