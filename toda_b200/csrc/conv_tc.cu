@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "epilogue.cuh"
+#include "table_slice.cuh"
 
 namespace {
 
@@ -389,11 +390,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
             if (use > 0) mbar_wait(idx_empty + 8 * ib, (use - 1) & 1);
             const uint32_t dst0 = idx_base + ib * kIdxBytes;
             const int row0 = t * kTileM;
-            for (int e = lane; e < kvol * kTileM; e += 32) {
-                const int k = e >> 7, r = e & (kTileM - 1);
-                if (row0 + r < n_out) cp_async_4(dst0 + 4 * e, nbr + (size_t)k * n_out + row0 + r);
-                else asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst0 + 4 * e), "r"(-1) : "memory");
-            }
+            load_table_slice<kTileM>(dst0, nbr, n_out, row0, n_out, kvol, lane);
             cp_async_arrive_noinc(idx_full + 8 * ib);
             mbar_arrive(idx_full + 8 * ib);
         }
@@ -501,9 +498,11 @@ int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int
     int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;   // persistent: one CTA per SM walks the tiles
     CUtensorMap map_w;
     if (int rc = conv_tma_make_map(&map_w, wb, (uint64_t)cout, (uint64_t)kvol * cin, (uint32_t)cout, kChunkK)) return rc;
-#define LAUNCH_TC(CI, CO)                                                                                                    \
+    // K blocks per chunk: 2 for Cout <= 64 unless TODA_TC_KB=1 (A/B measurements)
+    static int kb_env = -1;
+    if (kb_env < 0) { const char *e = getenv("TODA_TC_KB"); kb_env = e ? atoi(e) : 0; }
+#define LAUNCH_TC_KB(CI, CO, KB_)                                                                                            \
     do {                                                                                                                     \
-        constexpr int KB_ = (CO) <= 64 ? 2 : 1;                                                                              \
         constexpr int smem = FwdCfg<CO, KB_>::kSmem;                                                                         \
         static bool attr_set = false;                                                                                        \
         if (!attr_set) {                                                                                                     \
@@ -511,6 +510,11 @@ int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int
             attr_set = true;                                                                                                 \
         }                                                                                                                    \
         conv_tc_fwd_kernel<CI, CO, KB_><<<grid, kFwdThreads, smem, st>>>(xb, nbr, n_out, kvol, map_w, bias, y, bn_sums, num_tiles, g_dbg_timeline); \
+    } while (0)
+#define LAUNCH_TC(CI, CO)                                                                                                    \
+    do {                                                                                                                     \
+        if ((CO) <= 64 && kb_env != 1) LAUNCH_TC_KB(CI, CO, ((CO) <= 64 ? 2 : 1));                                           \
+        else LAUNCH_TC_KB(CI, CO, 1);                                                                                        \
     } while (0)
 #define LAUNCH_TC_CO(CI)                                                                                 \
     switch (cout) {                                                                                      \
@@ -529,6 +533,7 @@ int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int
     }
 #undef LAUNCH_TC_CO
 #undef LAUNCH_TC
+#undef LAUNCH_TC_KB
     TODA_LAUNCH_OK();
     return TODA_OK;
 }
@@ -805,11 +810,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) conv_tc_wgrad_kernel(const _
             if (use > 0) mbar_wait(idx_empty + 8 * ib, (use - 1) & 1);
             const uint32_t dst0 = idx_base + ib * kIdxW;
             const int row_base = r_begin + rc * kRowsW;
-            for (int e = lane; e < noffs * kRowsW; e += 32) {
-                const int koff = e / kRowsW, r = e & (kRowsW - 1);
-                if (row_base + r < r_end) cp_async_4(dst0 + 4 * e, nbr + (size_t)(k0 + koff) * n_out + row_base + r);
-                else asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst0 + 4 * e), "r"(-1) : "memory");
-            }
+            load_table_slice<ROWS>(dst0, nbr + (size_t)k0 * n_out, n_out, row_base, r_end, noffs, lane);
             cp_async_arrive_noinc(idx_full + 8 * ib);
             mbar_arrive(idx_full + 8 * ib);
         }

@@ -15,6 +15,7 @@
 
 #include "common.cuh"
 #include "epilogue.cuh"
+#include "table_slice.cuh"
 
 namespace {
 
@@ -302,11 +303,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_fwd_kernel(const __grid_
             if (use > 0) mbar_wait(idx_empty + 8 * ib, (use - 1) & 1);
             const uint32_t dst0 = idx_base + ib * kIdxBytes;
             const int row0 = t * kTileM;
-            for (int e = lane; e < kvol * kTileM; e += 32) {
-                const int k = e >> 7, r = e & (kTileM - 1);
-                if (row0 + r < n_out) cp_async_4(dst0 + 4 * e, nbr + (size_t)k * n_out + row0 + r);
-                else asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst0 + 4 * e), "r"(-1) : "memory");
-            }
+            load_table_slice<kTileM>(dst0, nbr, n_out, row0, n_out, kvol, lane);
             cp_async_arrive_noinc(idx_full + 8 * ib);
             mbar_arrive(idx_full + 8 * ib);
         }
