@@ -322,6 +322,8 @@ def run_ours(args, rank, world, local_rank):
         return None
     # ---- roofline pass (rank 0): per-call device times of one more step, not part of `value` ----------------
     peaks = load_peaks()
+    step(*devs[0], reduce=False)                # (re-warms the allocator for the in-line call sequence)
+    torch.cuda.synchronize()
     ops.profile_begin()
     loss, bd = step(*devs[0], reduce=False)     # rank 0 only: no collective inside this pass
     prof = ops.profile_end()
