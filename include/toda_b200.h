@@ -64,6 +64,32 @@ int toda_index_rows(const void *index, int batch, int D, int H, int W, const int
 int toda_index_release(void *index, int batch, int D, int H, int W, const int32_t *coords, int n, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K0 point-stream selection (order-preserving compaction under a per-point predicate).  Replaces, for the points of a
+ * whole batch of frames in one call, the boolean-mask indexing of
+ *   mode TODA_SELECT_RANGE_XY  common_utils.mask_points_by_range (pcdet/utils/common_utils.py L60-63) as used by
+ *        DataProcessor.mask_points_and_boxes_outside_range (data_processor.py L78-91): lo <= x,y <= hi, no z test;
+ *        params_host = {lo_x, lo_y, hi_x, hi_y} (compared in float32, as the reference's float32 range array is)
+ *   mode TODA_SELECT_RECT_XY   the crop of inter_domain_point_cutmix (inter_domain_point_cutmix.py L45-55): strict
+ *        min < x,y < max with float64 thresholds; params_host = {min_x, min_y, max_x, max_y}
+ *   mode TODA_SELECT_SECTOR    the sector of PolarMix swap / swap_with_range (inter_domain_point_polarmix.py L76-80,
+ *        L103-119): start < -arctan2(y,x) < end in float32; params_host = {start, end, dis_th, dis_mode} with
+ *        dis_mode 0 = no distance test, 1 = also sqrt(x^2+y^2) < dis_th, 2 = also > dis_th
+ * invert != 0 keeps the complement (np.delete / ~mask).  Kept rows keep their input order (what numpy's mask indexing
+ * gives).  add_batch_col != 0 prepends the frame index as a float column (collate_batch, dataset.py L173-178), so raw
+ * (N,F) frames can be shipped and collated on the device.
+ *   points [n][stride] fp32, x at column x_col and y at x_col+1; frame_offsets int32[batch+1] device or NULL
+ *   out [>= n][stride + (add_batch_col?1:0)]; out_offsets int32[batch+1] device (kept rows before each frame start,
+ *   last entry = total kept) or int32[1] = total when frame_offsets is NULL.
+ * ------------------------------------------------------------------------------------------ */
+#define TODA_SELECT_RANGE_XY 0
+#define TODA_SELECT_RECT_XY 1
+#define TODA_SELECT_SECTOR 2
+size_t toda_points_select_workspace_bytes(int n);
+int toda_points_select(const float *points, int n, int stride, int x_col, const int32_t *frame_offsets, int batch, int mode,
+                       const double *params_host, int invert, int add_batch_col, float *out, int32_t *out_offsets,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * K1 hard voxelizer.  Replaces spconv.utils.Point2VoxelCPU3d.point_to_voxel as called from
  * pcdet/datasets/processor/data_processor.py L36-42, L54 (VoxelGeneratorWrapper) /
  * L115-143 (transform_points_to_voxels), for a whole batch of frames in one call.

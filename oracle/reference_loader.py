@@ -97,9 +97,32 @@ def load(provider_modules, root=REF_ROOT):
                                   f"{P}/models/backbones_2d/map_to_bev/height_compression.py")
     ns.spconv_backbone = _load("pcdet.models.backbones_3d.spconv_backbone",
                                f"{P}/models/backbones_3d/spconv_backbone.py")
+    ns.load_mixers = lambda: _load_mixers(ns, P)
     ns.DataProcessor = ns.data_processor.DataProcessor
     ns.MeanVFE = ns.mean_vfe.MeanVFE
     ns.HeightCompression = ns.height_compression.HeightCompression
     ns.VoxelBackBone8x = ns.spconv_backbone.VoxelBackBone8x
     ns.VoxelResBackBone8x = ns.spconv_backbone.VoxelResBackBone8x
+    return ns
+
+
+def _load_mixers(ns, P):
+    """The reference's point mixers, loaded on demand: they import the compiled iou3d_nms
+    extension, which the point-level code paths exercised by the golden generator never call -- stubbed."""
+    for name in ["pcdet.ops.iou3d_nms", "pcdet.datasets.augmentor"]:
+        if name not in sys.modules:
+            _pkg(name)
+            parent, _, leaf = name.rpartition(".")
+            setattr(sys.modules[parent], leaf, sys.modules[name])
+    stub = types.ModuleType("pcdet.ops.iou3d_nms.iou3d_nms_utils")
+    sys.modules["pcdet.ops.iou3d_nms.iou3d_nms_utils"] = stub
+    sys.modules["pcdet.ops.iou3d_nms"].iou3d_nms_utils = stub
+    aug = types.ModuleType("pcdet.datasets.augmentor.augmentor_utils")
+    aug.get_points_in_box = None      # only used by the collision-detection variant, not exercised
+    sys.modules["pcdet.datasets.augmentor.augmentor_utils"] = aug
+    sys.modules["pcdet.datasets.augmentor"].augmentor_utils = aug
+    ns.cutmix = _load("pcdet.datasets.processor.inter_domain_point_cutmix", f"{P}/datasets/processor/inter_domain_point_cutmix.py")
+    ns.polarmix = _load("pcdet.datasets.processor.inter_domain_point_polarmix",
+                        f"{P}/datasets/processor/inter_domain_point_polarmix.py")
+    ns.mixup = _load("pcdet.datasets.processor.intra_domain_point_mixup", f"{P}/datasets/processor/intra_domain_point_mixup.py")
     return ns

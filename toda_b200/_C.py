@@ -23,6 +23,9 @@ SIGNATURES = {
     "toda_index_build": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp]),
     "toda_index_rows": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp]),
     "toda_index_release": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]),
+    "toda_points_select_workspace_bytes": (c_sz, [c_int]),
+    "toda_points_select": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_int, c_int, ctypes.POINTER(ctypes.c_double), c_int, c_int,
+                                   c_vp, c_vp, c_vp, c_sz, c_vp]),
     "toda_voxelize_workspace_bytes": (c_sz, [c_i64, c_int, _IP, c_int, c_int]),
     "toda_voxelize_hard": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_int, _FP, _FP, _IP, c_int, c_int,
                                    c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
@@ -79,6 +82,10 @@ def check(rc, what=""):
 
 def ints(vals):
     return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def doubles(vals):
+    return (ctypes.c_double * len(vals))(*[float(v) for v in vals])
 
 
 def floats(vals):

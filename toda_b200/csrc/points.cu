@@ -1,0 +1,198 @@
+// K0 point-stream selection: order-preserving compaction of a collated point cloud under a per-point predicate.
+// Restates the point side of the reference's host pre-steps so that raw frames can stay on the GPU:
+//   mode 0  range mask     pcdet/utils/common_utils.py L60-63 via data_processor.py L78-91 (x, y inclusive, no z test)
+//   mode 1  rectangle      inter_domain_point_cutmix.py L45-55 (strict, thresholds in float64 as numpy promotes them)
+//   mode 2  polar sector   inter_domain_point_polarmix.py L76-80 / L103-119 (yaw = -arctan2(y, x) in float32,
+//                          strict; optional distance test against dis_th)
+// `invert` keeps the complement (np.delete / ~mask).  Optionally the batch-index column of collate_batch
+// (dataset.py L173-178) is written in the same pass (`add_batch_col`), so the host can ship raw (N,F) frames.
+// Two launches, no atomics, no inter-CTA waiting: tile = 1024 points; launch 1 writes the ballot words and per-tile
+// counts, launch 2 sums the counts of the tiles before it, ranks by popcount and copies rows.  HBM-bound:
+// algorithmic bytes = 4*stride*N read + 4*(stride+add)*N' written.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kSelThreads = 256;
+constexpr int kSelTile = 1024;                 // points per CTA = 4 per thread = 32 ballot words
+
+struct SelParams {
+    int mode, invert;
+    float lo_x, lo_y, hi_x, hi_y;              // mode 0
+    double min_x, min_y, max_x, max_y;         // mode 1
+    float start, end, dis_th;                  // mode 2
+    int dis_mode;                              // 0 none, 1 keep dis < dis_th, 2 keep dis > dis_th
+};
+
+__device__ __forceinline__ bool sel_keep(const SelParams &p, float x, float y) {
+    bool k;
+    if (p.mode == 0) {
+        k = x >= p.lo_x && x <= p.hi_x && y >= p.lo_y && y <= p.hi_y;
+    } else if (p.mode == 1) {
+        const double xd = (double)x, yd = (double)y;
+        k = xd < p.max_x && yd < p.max_y && xd > p.min_x && yd > p.min_y;
+    } else {
+        // float32 result of arctan2 as numpy computes it for float32 inputs; evaluated in double and rounded once
+        const float yaw = -(float)atan2((double)y, (double)x);
+        k = yaw > p.start && yaw < p.end;
+        if (p.dis_mode) {
+            const float dis = __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)));   // np.sqrt(x**2 + y**2), float32
+            k = k && (p.dis_mode == 1 ? dis < p.dis_th : dis > p.dis_th);
+        }
+    }
+    return k != (p.invert != 0);
+}
+
+__global__ void __launch_bounds__(kSelThreads) select_flag_kernel(const float *__restrict__ points, int n, int stride, int x_col,
+                                                                  SelParams p, uint32_t *__restrict__ words,
+                                                                  int *__restrict__ tile_counts) {
+    __shared__ int warp_cnt[kSelThreads / 32];
+    const int tile0 = blockIdx.x * kSelTile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < kSelTile / kSelThreads; ++j) {
+        const int i = tile0 + j * kSelThreads + threadIdx.x;      // a warp covers 32 consecutive points = one word
+        bool k = false;
+        if (i < n) {
+            const float *row = points + (size_t)i * stride + x_col;
+            k = sel_keep(p, __ldg(row), __ldg(row + 1));
+        }
+        const uint32_t w = __ballot_sync(0xffffffffu, k);
+        if (lane == 0) {
+            words[(tile0 >> 5) + j * (kSelThreads / 32) + warp] = w;
+            cnt += __popc(w);
+        }
+    }
+    if (lane == 0) warp_cnt[warp] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < kSelThreads / 32; ++w) t += warp_cnt[w];
+        tile_counts[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(kSelThreads) select_copy_kernel(const float *__restrict__ points, int n, int stride,
+                                                                  const uint32_t *__restrict__ words,
+                                                                  const int *__restrict__ tile_counts,
+                                                                  const int32_t *__restrict__ frame_offsets, int batch,
+                                                                  int add_batch_col, float *__restrict__ out,
+                                                                  int32_t *__restrict__ out_offsets) {
+    __shared__ int warp_sums[kSelThreads / 32];
+    __shared__ int tile_offset_s;
+    __shared__ int word_prefix[kSelTile / 32 + 1];
+    __shared__ int frame_lo[65];               // frame_offsets (batch <= 64)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int part = 0;
+    for (int j = threadIdx.x; j < (int)blockIdx.x; j += kSelThreads) part += tile_counts[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) warp_sums[warp] = part;
+    if (frame_offsets && (int)threadIdx.x <= batch) frame_lo[threadIdx.x] = frame_offsets[threadIdx.x];
+    __syncthreads();
+    const int tile0 = blockIdx.x * kSelTile;
+    if (threadIdx.x == 0) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < kSelThreads / 32; ++w) t += warp_sums[w];
+        tile_offset_s = t;
+        // exclusive prefix over this tile's 32 words
+        int run = 0;
+        for (int w = 0; w < kSelTile / 32; ++w) {
+            word_prefix[w] = run;
+            const int i0 = tile0 + 32 * w;
+            run += i0 < n ? __popc(words[(tile0 >> 5) + w]) : 0;
+        }
+        word_prefix[kSelTile / 32] = run;
+    }
+    __syncthreads();
+    const int tile_offset = tile_offset_s;
+    // new frame boundaries: kept points before frame_offsets[b]
+    if (out_offsets) {
+        if (frame_offsets) {
+            if ((int)threadIdx.x <= batch) {
+                const int fo = frame_lo[threadIdx.x];
+                const bool mine = (fo >= tile0 && fo < tile0 + kSelTile && fo < n) || (fo >= n && tile0 <= n - 1 && n - 1 < tile0 + kSelTile) ||
+                                  (n == 0 && blockIdx.x == 0);
+                if (mine) {
+                    int v;
+                    if (fo >= n) {
+                        v = tile_offset + word_prefix[kSelTile / 32];      // total (this is the last tile)
+                    } else {
+                        const int rel = fo - tile0, w = rel >> 5, b = rel & 31;
+                        v = tile_offset + word_prefix[w] + __popc(words[(tile0 >> 5) + w] & ((1u << b) - 1u));
+                    }
+                    out_offsets[threadIdx.x] = v;
+                }
+            }
+        } else if (threadIdx.x == 0 && (tile0 + kSelTile >= n)) {
+            out_offsets[0] = tile_offset + word_prefix[kSelTile / 32];
+        }
+    }
+    const int out_stride = stride + (add_batch_col ? 1 : 0);
+#pragma unroll
+    for (int j = 0; j < kSelTile / kSelThreads; ++j) {
+        const int i = tile0 + j * kSelThreads + threadIdx.x;
+        if (i >= n) continue;
+        const int wi = j * (kSelThreads / 32) + warp;
+        const uint32_t w = words[(tile0 >> 5) + wi];
+        if (!((w >> lane) & 1u)) continue;
+        const int dst = tile_offset + word_prefix[wi] + __popc(w & ((1u << lane) - 1u));
+        const float *src = points + (size_t)i * stride;
+        float *o = out + (size_t)dst * out_stride;
+        if (add_batch_col) {
+            int b = 0;
+            if (frame_offsets) {
+                // frame of point i: last b with frame_lo[b] <= i (batch is small)
+                for (int q = 1; q < batch; ++q) b += (i >= frame_lo[q]) ? 1 : 0;
+            }
+            *o++ = (float)b;
+        }
+        for (int c = 0; c < stride; ++c) o[c] = __ldg(src + c);
+    }
+}
+
+}  // namespace
+
+extern "C" size_t toda_points_select_workspace_bytes(int n) {
+    if (n < 0) return 0;
+    size_t tiles = (size_t)ceil_div(n > 0 ? n : 1, kSelTile);
+    return align_up(tiles * (kSelTile / 32) * sizeof(uint32_t), 256) + align_up(tiles * sizeof(int), 256) + 256;
+}
+
+extern "C" int toda_points_select(const float *points, int n, int stride, int x_col, const int32_t *frame_offsets, int batch,
+                                  int mode, const double *params_host, int invert, int add_batch_col, float *out,
+                                  int32_t *out_offsets, void *workspace, size_t workspace_bytes, void *stream) {
+    TODA_CHECK_ARG(n >= 0 && stride >= 2 && x_col >= 0 && x_col + 1 < stride, "points_select: bad layout n=%d stride=%d x_col=%d", n, stride, x_col);
+    TODA_CHECK_ARG(mode >= 0 && mode <= 2 && params_host, "points_select: bad mode %d", mode);
+    TODA_CHECK_ARG(!frame_offsets || (batch >= 1 && batch <= 64), "points_select: batch %d outside [1, 64]", batch);
+    TODA_CHECK_ARG(out_offsets && workspace && (n == 0 || (points && out)), "points_select: null pointer");
+    if (workspace_bytes < toda_points_select_workspace_bytes(n)) {
+        toda_set_error("points_select: workspace %zu < required %zu bytes", workspace_bytes, toda_points_select_workspace_bytes(n));
+        return TODA_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    SelParams p = {};
+    p.mode = mode;
+    p.invert = invert;
+    if (mode == 0) {
+        p.lo_x = (float)params_host[0]; p.lo_y = (float)params_host[1]; p.hi_x = (float)params_host[2]; p.hi_y = (float)params_host[3];
+    } else if (mode == 1) {
+        p.min_x = params_host[0]; p.min_y = params_host[1]; p.max_x = params_host[2]; p.max_y = params_host[3];
+    } else {
+        p.start = (float)params_host[0]; p.end = (float)params_host[1]; p.dis_th = (float)params_host[2];
+        p.dis_mode = (int)params_host[3];
+        TODA_CHECK_ARG(p.dis_mode >= 0 && p.dis_mode <= 2, "points_select: bad distance mode");
+    }
+    const int tiles = ceil_div(n > 0 ? n : 1, kSelTile);
+    uint32_t *words = (uint32_t *)workspace;
+    int *tile_counts = (int *)((char *)workspace + align_up((size_t)tiles * (kSelTile / 32) * sizeof(uint32_t), 256));
+    select_flag_kernel<<<tiles, kSelThreads, 0, st>>>(points, n, stride, x_col, p, words, tile_counts);
+    TODA_LAUNCH_OK();
+    select_copy_kernel<<<tiles, kSelThreads, 0, st>>>(points, n, stride, words, tile_counts, frame_offsets, batch, add_batch_col,
+                                                      out, out_offsets);
+    TODA_LAUNCH_OK();
+    return TODA_OK;
+}

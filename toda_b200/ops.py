@@ -116,6 +116,54 @@ def _workspace(tag, nbytes, device, zero=False):
 
 
 # ------------------------------------------------------------------------------------------------
+# K0 point-stream selection
+# ------------------------------------------------------------------------------------------------
+SELECT_RANGE_XY, SELECT_RECT_XY, SELECT_SECTOR = 0, 1, 2
+
+
+def points_select(points, frame_offsets, mode, params, invert=False, add_batch_col=False, x_col=0, trim=True):
+    """Order-preserving selection of point rows (numpy `points[mask]` for a whole batch of frames).
+
+    points (N, stride) float32 CUDA; frame_offsets int32 (B+1) CUDA tensor or None.  mode / params: see
+    include/toda_b200.h (range mask of common_utils.mask_points_by_range, cutmix rectangle, PolarMix sector).
+    Returns (rows, offsets): rows (N', stride[+1]) and int32 offsets (B+1) (or (1,) = N' without frames).
+    trim=True slices to N' (one host sync); trim=False returns the capacity-sized buffer.
+    """
+    points = _need(points, torch.float32, "points")
+    assert points.dim() == 2
+    n, stride = points.shape
+    dev = points.device
+    batch = 0
+    if frame_offsets is not None:
+        frame_offsets = _need(frame_offsets, torch.int32, "frame_offsets")
+        batch = frame_offsets.numel() - 1
+    L = _C.lib()
+    ws = _workspace("select", L.toda_points_select_workspace_bytes(n), dev)
+    out = torch.empty((n, stride + (1 if add_batch_col else 0)), dtype=torch.float32, device=dev)
+    out_offsets = torch.empty((batch + 1,), dtype=torch.int32, device=dev)
+    p = list(params) + [0.0] * (4 - len(params))
+    with _timed("points_select", n=n, stride=stride, mode=int(mode)):
+        _C.check(L.toda_points_select(_p(points), n, stride, int(x_col), _p(frame_offsets), batch, int(mode), _C.doubles(p),
+                                      int(bool(invert)), int(bool(add_batch_col)), _p(out), _p(out_offsets), _p(ws),
+                                      ws.numel(), _stream()), "toda_points_select")
+    _count(2)
+    if trim:
+        return out[:int(out_offsets[-1].item())], out_offsets
+    return out, out_offsets
+
+
+def gather_point_rows(points, rows):
+    """out[i] = points[rows[i]] (numpy `points[idx]`): shuffle_points / mixup prefixes for a given index vector."""
+    points = _need(points, torch.float32, "points")
+    rows = _need(rows, torch.int32, "rows")
+    n, c = rows.shape[0], points.shape[1]
+    out = torch.empty((n, c), dtype=torch.float32, device=points.device)
+    _C.check(_C.lib().toda_gather_rows(_p(points), _p(rows), n, c, _p(out), _stream()), "toda_gather_rows")
+    _count(1)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # K1 voxelizer
 # ------------------------------------------------------------------------------------------------
 def grid_size_xyz(pc_range, voxel_size):
