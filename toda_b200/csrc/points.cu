@@ -84,6 +84,8 @@ __global__ void __launch_bounds__(kSelThreads) select_copy_kernel(const float *_
     __shared__ int tile_offset_s;
     __shared__ int word_prefix[kSelTile / 32 + 1];
     __shared__ int frame_lo[65];               // frame_offsets (batch <= 64)
+    __shared__ int kept_rows[kSelTile];
+    __shared__ uint32_t word_s[kSelTile / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int part = 0;
     for (int j = threadIdx.x; j < (int)blockIdx.x; j += kSelThreads) part += tile_counts[j];
@@ -93,19 +95,25 @@ __global__ void __launch_bounds__(kSelThreads) select_copy_kernel(const float *_
     if (frame_offsets && (int)threadIdx.x <= batch) frame_lo[threadIdx.x] = frame_offsets[threadIdx.x];
     __syncthreads();
     const int tile0 = blockIdx.x * kSelTile;
-    if (threadIdx.x == 0) {
-        int t = 0;
+    if (warp == 0) {
+        // exclusive prefix over this tile's 32 ballot words: one word per lane, warp scan
+        const uint32_t w = (tile0 + 32 * lane < n) ? words[(tile0 >> 5) + lane] : 0u;
+        word_s[lane] = w;
+        const int c = __popc(w);
+        int incl = c;
 #pragma unroll
-        for (int w = 0; w < kSelThreads / 32; ++w) t += warp_sums[w];
-        tile_offset_s = t;
-        // exclusive prefix over this tile's 32 words
-        int run = 0;
-        for (int w = 0; w < kSelTile / 32; ++w) {
-            word_prefix[w] = run;
-            const int i0 = tile0 + 32 * w;
-            run += i0 < n ? __popc(words[(tile0 >> 5) + w]) : 0;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        word_prefix[kSelTile / 32] = run;
+        word_prefix[lane] = incl - c;
+        if (lane == 31) word_prefix[kSelTile / 32] = incl;
+        if (lane == 0) {
+            int t = 0;
+#pragma unroll
+            for (int q = 0; q < kSelThreads / 32; ++q) t += warp_sums[q];
+            tile_offset_s = t;
+        }
     }
     __syncthreads();
     const int tile_offset = tile_offset_s;
@@ -122,7 +130,7 @@ __global__ void __launch_bounds__(kSelThreads) select_copy_kernel(const float *_
                         v = tile_offset + word_prefix[kSelTile / 32];      // total (this is the last tile)
                     } else {
                         const int rel = fo - tile0, w = rel >> 5, b = rel & 31;
-                        v = tile_offset + word_prefix[w] + __popc(words[(tile0 >> 5) + w] & ((1u << b) - 1u));
+                        v = tile_offset + word_prefix[w] + __popc(word_s[w] & ((1u << b) - 1u));
                     }
                     out_offsets[threadIdx.x] = v;
                 }
@@ -131,26 +139,40 @@ __global__ void __launch_bounds__(kSelThreads) select_copy_kernel(const float *_
             out_offsets[0] = tile_offset + word_prefix[kSelTile / 32];
         }
     }
+    // kept rows of this tile, in order, as a list in shared memory; then the tile's output range
+    // [tile_offset, tile_offset + count) x out_stride is written element by element: stores are fully coalesced and the
+    // loads walk neighbouring rows
     const int out_stride = stride + (add_batch_col ? 1 : 0);
 #pragma unroll
     for (int j = 0; j < kSelTile / kSelThreads; ++j) {
         const int i = tile0 + j * kSelThreads + threadIdx.x;
-        if (i >= n) continue;
         const int wi = j * (kSelThreads / 32) + warp;
-        const uint32_t w = words[(tile0 >> 5) + wi];
-        if (!((w >> lane) & 1u)) continue;
-        const int dst = tile_offset + word_prefix[wi] + __popc(w & ((1u << lane) - 1u));
-        const float *src = points + (size_t)i * stride;
-        float *o = out + (size_t)dst * out_stride;
+        const uint32_t w = word_s[wi];
+        if ((w >> lane) & 1u) kept_rows[word_prefix[wi] + __popc(w & ((1u << lane) - 1u))] = i;
+    }
+    __syncthreads();
+    const int count = word_prefix[kSelTile / 32];
+    const int total = count * out_stride;
+    const float inv = 1.0f / (float)out_stride;       // e < 1024 * out_stride: (e + 0.5) * inv truncates exactly for stride <= 64
+    float *o = out + (size_t)tile_offset * out_stride;
+    for (int e = threadIdx.x; e < total; e += kSelThreads) {
+        const int r = __float2int_rz(((float)e + 0.5f) * inv);
+        const int c = e - r * out_stride;
+        const int i = kept_rows[r];
+        float v;
         if (add_batch_col) {
-            int b = 0;
-            if (frame_offsets) {
-                // frame of point i: last b with frame_lo[b] <= i (batch is small)
-                for (int q = 1; q < batch; ++q) b += (i >= frame_lo[q]) ? 1 : 0;
+            if (c == 0) {
+                int b = 0;
+                if (frame_offsets)
+                    for (int q = 1; q < batch; ++q) b += (i >= frame_lo[q]) ? 1 : 0;   // frame of point i (batch is small)
+                v = (float)b;
+            } else {
+                v = __ldg(points + (size_t)i * stride + c - 1);
             }
-            *o++ = (float)b;
+        } else {
+            v = __ldg(points + (size_t)i * stride + c);
         }
-        for (int c = 0; c < stride; ++c) o[c] = __ldg(src + c);
+        o[e] = v;
     }
 }
 
@@ -165,7 +187,7 @@ extern "C" size_t toda_points_select_workspace_bytes(int n) {
 extern "C" int toda_points_select(const float *points, int n, int stride, int x_col, const int32_t *frame_offsets, int batch,
                                   int mode, const double *params_host, int invert, int add_batch_col, float *out,
                                   int32_t *out_offsets, void *workspace, size_t workspace_bytes, void *stream) {
-    TODA_CHECK_ARG(n >= 0 && stride >= 2 && x_col >= 0 && x_col + 1 < stride, "points_select: bad layout n=%d stride=%d x_col=%d", n, stride, x_col);
+    TODA_CHECK_ARG(n >= 0 && stride >= 2 && stride <= 63 && x_col >= 0 && x_col + 1 < stride, "points_select: bad layout n=%d stride=%d x_col=%d", n, stride, x_col);
     TODA_CHECK_ARG(mode >= 0 && mode <= 2 && params_host, "points_select: bad mode %d", mode);
     TODA_CHECK_ARG(!frame_offsets || (batch >= 1 && batch <= 64), "points_select: batch %d outside [1, 64]", batch);
     TODA_CHECK_ARG(out_offsets && workspace && (n == 0 || (points && out)), "points_select: null pointer");
