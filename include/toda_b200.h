@@ -139,6 +139,14 @@ int toda_rulebook_sparse(const void *index_in, int iD, int iH, int iW, const voi
                          const int *ksize_host, const int *stride_host, const int *pad_host, int32_t *nbr_fwd,
                          int32_t *nbr_bwd, void *stream);
 
+/* Parity order of the input rows of a strided convolution: rows sorted by ((z+pz)%sz, (y+py)%sy, (x+px)%sx), canonical
+ * order kept inside a class (stable, deterministic); order[i] = canonical row at sorted position i, pos_of_row (optional)
+ * its inverse.  coords int32 (n,4) = (b,z,y,x).  At most 8 classes (strides <= 2).  Used by the dgrad of SparseConv3d
+ * (see out_rows / tile_masks of toda_spconv_fwd). */
+size_t toda_parity_order_workspace_bytes(int n);
+int toda_parity_order(const int32_t *coords, int n, const int *stride_host, const int *pad_host, int32_t *order,
+                      int32_t *pos_of_row, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * K5/K6/K7 sparse convolution on neighbour tables (every `conv(x)` in spconv_backbone.py).
  *   fwd :  y[o,:]  = bias + sum_k x[nbr[k,o],:] @ w[k]        w: [kvol, Cin, Cout]
@@ -162,10 +170,21 @@ size_t toda_spconv_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol, in
 /* bn_sums (optional, may be NULL; tensor-core kernel only, see toda_spconv_uses_tensor_cores): double[2*cout] receiving
  * sum(y) and sum(y*y) per output channel, accumulated in the epilogue, for toda_bn_finalize_sums -- the BatchNorm that
  * follows the convolution (spconv_backbone.py L23-24) then needs no statistics pass over y. */
+/* out_rows (optional, may be NULL): int32[n_out]; output row o of this call is written to y[out_rows[o], :] instead of
+ * y[o, :].  Used by the dgrad of strided convolutions: with stride s only the offsets k = (in + pad) mod s (per axis) can
+ * reach an input voxel, so its rows are processed in s_z*s_y*s_x parity classes, each with the compact table of its own
+ * 1..kvol offsets: the caller sorts the rows (and the table's columns) by class and they are scattered back to
+ * canonical rows here; with tile_masks the K blocks that are structurally empty for a class are skipped (in canonical
+ * order every tile mixes all classes and the [27] table is ~85 % structural padding).
+ * tile_masks (optional, may be NULL): uint32[ceil(n_out/128)] from toda_table_tile_masks -- bit k set when some row of
+ * that 128-row tile has a neighbour under offset k; the tensor-core kernel then walks only the K blocks that hold data
+ * (the FFMA kernel tests this per tile itself). */
+int toda_table_tile_masks(const int32_t *nbr, int n_out, int kvol, uint32_t *masks, void *stream);
 int toda_spconv_uses_tensor_cores(int cin, int cout, int kvol, int precision);
 int toda_spconv_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
-                    const float *w, int cout, const float *bias, float *y, double *bn_sums, int precision, void *workspace,
-                    size_t workspace_bytes, void *stream);
+                    const float *w, int cout, const float *bias, float *y, const int32_t *out_rows,
+                    const uint32_t *tile_masks, double *bn_sums, int precision, void *workspace, size_t workspace_bytes,
+                    void *stream);
 size_t toda_spconv_wgrad_workspace_bytes(int n_in, int n_out, int kvol, int cin, int cout, int precision);
 int toda_spconv_wgrad(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
                       const float *dy, const void *dy_bf16, int cout, float *dw_param, void *workspace,

@@ -49,7 +49,7 @@ def test_argument_errors_are_reported_not_ignored(built):
     lib = built.lib()
     rc = lib.toda_mean_vfe_fwd(None, None, 0, 10, 0, 5, None, None)
     assert rc == -1 and b"mean_vfe_fwd" in lib.toda_last_error()
-    rc = lib.toda_spconv_fwd(None, None, 0, 0, None, 5, 27, None, 16, None, None, None, 0, None, 0, None)
+    rc = lib.toda_spconv_fwd(None, None, 0, 0, None, 5, 27, None, 16, None, None, None, None, None, 0, None, 0, None)
     assert rc == -1
 
 

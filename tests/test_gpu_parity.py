@@ -335,3 +335,27 @@ def test_compat_shim_runs_sequential_with_fused_bn():
     assert np.array_equal(yb.indices.cpu().numpy(), ya.indices.numpy())
     PU.assert_close(yb.features.detach().cpu().numpy(), ya.features.detach().numpy(), what="sequential")
     PU.assert_close(yb.dense().detach().cpu().numpy(), ya.dense().detach().numpy(), what="dense")
+
+
+@pytest.mark.parametrize("stride,padding,n", [((2, 2, 2), (1, 1, 1), 70001), ((2, 2, 2), (0, 1, 1), 1024), ((2, 1, 1), (0, 0, 0), 5000),
+                                              ((1, 2, 1), (0, 1, 0), 33)])
+def test_parity_order_is_a_stable_class_sort(stride, padding, n):
+    """toda_parity_order == numpy stable argsort of the class code; the tile masks of the class-sorted table agree with it."""
+    from toda_b200 import ops
+    rng = np.random.default_rng(n)
+    coords = np.stack([rng.integers(0, 3, n), rng.integers(0, 41, n), rng.integers(0, 300, n), rng.integers(0, 300, n)], 1).astype(np.int32)
+    cls = np.zeros(n, np.int64)
+    for a in range(3):
+        cls = cls * stride[a] + (coords[:, 1 + a] + padding[a]) % stride[a]
+    want = np.argsort(cls, kind="stable")
+    c = torch.from_numpy(coords).cuda()
+    table = torch.from_numpy(rng.integers(-1, 50, (27, n)).astype(np.int32) * (rng.random((27, n)) < 0.05) - (rng.random((27, n)) >= 0.5)).int().cuda()
+    order, sorted_table = ops._dgrad_parity_order(c, table, list(stride), list(padding))
+    assert np.array_equal(order.cpu().numpy(), want)
+    assert torch.equal(sorted_table, table[:, order.long()])
+    masks = ops.table_tile_masks(sorted_table).cpu().numpy().astype(np.uint32)
+    t = sorted_table.cpu().numpy()
+    for tile in range((n + 127) // 128):
+        blk = t[:, tile * 128:(tile + 1) * 128]
+        want_mask = sum((1 << k) for k in range(27) if (blk[k] >= 0).any())
+        assert int(masks[tile]) == want_mask, tile

@@ -6,7 +6,8 @@
 #include "common.cuh"
 
 int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *w,
-                int cout, const float *bias, float *y, double *bn_sums, void *workspace, size_t workspace_bytes,
+                int cout, const float *bias, float *y, const int32_t *out_rows, const uint32_t *tile_masks, double *bn_sums,
+                void *workspace, size_t workspace_bytes,
                 cudaStream_t st);
 size_t conv_tc_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol);
 int conv_tc_wgrad(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
@@ -26,7 +27,8 @@ template <int BM, int BN>
 __global__ void __launch_bounds__(kThreads) conv_fwd_f32_kernel(const float *__restrict__ x, int cin,
                                                                 const int *__restrict__ nbr, int n_out, int kvol,
                                                                 const float *__restrict__ w, int cout,
-                                                                const float *__restrict__ bias, float *__restrict__ y) {
+                                                                const float *__restrict__ bias, float *__restrict__ y,
+                                                                const int *__restrict__ out_rows /* optional */) {
     static_assert((BM / 4) * (BN / 4) == kThreads, "4x4 micro-tiles must cover the CTA tile");
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN + 4];
@@ -90,10 +92,11 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_f32_kernel(const float *__r
     for (int i = 0; i < 4; ++i) {
         int r = row0 + ty * 4 + i;
         if (r >= n_out) continue;
+        const int orow = out_rows ? __ldg(out_rows + r) : r;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int c = col0 + tx * 4 + j;
-            if (c < cout) y[(size_t)r * cout + c] = acc[i][j] + (bias ? __ldg(bias + c) : 0.f);
+            if (c < cout) y[(size_t)orow * cout + c] = acc[i][j] + (bias ? __ldg(bias + c) : 0.f);
         }
     }
 }
@@ -261,7 +264,8 @@ extern "C" size_t toda_spconv_fwd_workspace_bytes(int n_in, int cin, int cout, i
 }
 
 extern "C" int toda_spconv_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
-                               const float *w, int cout, const float *bias, float *y, double *bn_sums, int precision,
+                               const float *w, int cout, const float *bias, float *y, const int32_t *out_rows,
+                               const uint32_t *tile_masks, double *bn_sums, int precision,
                                void *workspace, size_t workspace_bytes, void *stream) {
     TODA_CHECK_ARG(n_in >= 0 && n_out >= 0 && cin > 0 && cout > 0 && kvol > 0, "spconv_fwd: bad sizes");
     if (n_out == 0) return TODA_OK;
@@ -271,17 +275,18 @@ extern "C" int toda_spconv_fwd(const float *x, const void *x_bf16, int n_in, int
     // kernel selection by shape: the tensor-core kernel covers Cin in {<=16 (zero-padded to 16), 32, 64, 128} and
     // Cout in {16,32,64,128}; anything else (e.g. the dgrad of the 4/5-channel input layer) runs on the FFMA kernel.
     if (precision == TODA_CONV_BF16 && conv_tc_supported(cin, cout, kvol))
-        return conv_tc_fwd(x, x_bf16, n_in, cin, nbr, n_out, kvol, w, cout, bias, y, bn_sums, workspace, workspace_bytes, st);
+        return conv_tc_fwd(x, x_bf16, n_in, cin, nbr, n_out, kvol, w, cout, bias, y, out_rows, tile_masks, bn_sums, workspace,
+                           workspace_bytes, st);
     TODA_CHECK_ARG(!bn_sums, "spconv_fwd: fused BatchNorm statistics need the tensor-core kernel for this shape");
     if (cout <= 16) {
         dim3 grid(ceil_div(n_out, 256), ceil_div(cout, 16));
-        conv_fwd_f32_kernel<256, 16><<<grid, kThreads, 0, st>>>(x, cin, nbr, n_out, kvol, w, cout, bias, y);
+        conv_fwd_f32_kernel<256, 16><<<grid, kThreads, 0, st>>>(x, cin, nbr, n_out, kvol, w, cout, bias, y, out_rows);
     } else if (cout <= 32) {
         dim3 grid(ceil_div(n_out, 128), ceil_div(cout, 32));
-        conv_fwd_f32_kernel<128, 32><<<grid, kThreads, 0, st>>>(x, cin, nbr, n_out, kvol, w, cout, bias, y);
+        conv_fwd_f32_kernel<128, 32><<<grid, kThreads, 0, st>>>(x, cin, nbr, n_out, kvol, w, cout, bias, y, out_rows);
     } else {
         dim3 grid(ceil_div(n_out, 64), ceil_div(cout, 64));
-        conv_fwd_f32_kernel<64, 64><<<grid, kThreads, 0, st>>>(x, cin, nbr, n_out, kvol, w, cout, bias, y);
+        conv_fwd_f32_kernel<64, 64><<<grid, kThreads, 0, st>>>(x, cin, nbr, n_out, kvol, w, cout, bias, y, out_rows);
     }
     TODA_LAUNCH_OK();
     return TODA_OK;

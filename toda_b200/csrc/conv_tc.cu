@@ -167,6 +167,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
                                                                      const int *__restrict__ nbr, int n_out, int kvol,
                                                                      const __grid_constant__ CUtensorMap map_w /*[COUT][kvol*CIN] bf16*/,
                                                                      const float *__restrict__ bias, float *__restrict__ y,
+                                                                     const int *__restrict__ out_rows /* optional */,
+                                                                     const uint32_t *__restrict__ tile_masks /* optional */,
                                                                      double *__restrict__ bn_sums, int num_tiles,
                                                                      long long *__restrict__ dbg) {
     static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 128, "UMMA N");
@@ -188,6 +190,24 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ktot = kvol * CIN;
     const int nchunks = (ktot + kChunkElems - 1) / kChunkElems;
+    // K chunks of tile t that hold at least one real neighbour (bit c = chunk c), from the tile's offset mask.  Every role
+    // derives the same list, so the stage ring stays in step.  Without masks every chunk is walked.  A tile with no
+    // neighbour at all still walks chunk 0 (all zero rows) so that its accumulator is defined.
+    auto chunk_mask_of = [&](int t) -> unsigned long long {
+        if (!tile_masks) return nchunks >= 64 ? ~0ull : ((1ull << nchunks) - 1ull);
+        const uint32_t om = __ldg(tile_masks + t);
+        unsigned long long cm = 0ull;
+        if (CIN <= kChunkElems) {
+            constexpr int kOpc = CIN <= kChunkElems ? kChunkElems / CIN : 1;       // offsets per chunk
+            for (int c = 0; c < nchunks; ++c)
+                if ((om >> (c * kOpc)) & ((1u << kOpc) - 1u)) cm |= 1ull << c;
+        } else {
+            constexpr int kCpo = CIN > kChunkElems ? CIN / kChunkElems : 1;        // chunks per offset
+            for (int c = 0; c < nchunks; ++c)
+                if ((om >> (c / kCpo)) & 1u) cm |= 1ull << c;
+        }
+        return cm ? cm : 1ull;
+    };
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
@@ -232,7 +252,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
             const int ib = it & 1;
             mbar_wait(idx_full + 8 * ib, (it >> 1) & 1);
             const uint32_t idx_tile = idx_lane + ib * kIdxBytes;
-            for (int c = 0; c < nchunks; ++c, ++g) {
+            for (unsigned long long cm = chunk_mask_of(t); cm; cm &= cm - 1, ++g) {
+                const int c = __ffsll((long long)cm) - 1;
                 const int s = g % S, use = g / S;
                 if (use > 0) mbar_wait(empty_bar + 8 * s, (use - 1) & 1);
                 const uint32_t a_dst0 = base + s * C::kStage + piece_off;
@@ -299,7 +320,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
                 const int ab = it & 1, ause = it >> 1;
                 if (ause > 0) mbar_wait(acc_empty + 8 * ab, (ause - 1) & 1);   // epilogue has drained this accumulator
                 const uint32_t d_tmem = tmem_base + ab * COUT;
-                for (int c = 0; c < nchunks; ++c, ++g) {
+                uint32_t accumulate = 0;
+                for (unsigned long long cm = chunk_mask_of(t); cm; cm &= cm - 1, ++g) {
+                    const int c = __ffsll((long long)cm) - 1;
                     const int s = g % S, use = g / S;
                     if (dbg && blockIdx.x == 0 && lane == 0 && g < 256) dbg[4 * 256 + g] = clock64();
                     if (!ready) mbar_wait(full_bar + 8 * s, use & 1);
@@ -314,13 +337,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
                         // one descriptor per operand per chunk; a K-step advances the start-address field by 32 B (>>4 = 2),
                         // the second 64-element K block starts one A / B block further
                         const uint64_t ad0 = make_desc_k_sw128(a_tile), bd0 = make_desc_k_sw128(b_tile);
-                        umma_bf16(d_tmem, ad0, bd0, idesc, c != 0);
+                        umma_bf16(d_tmem, ad0, bd0, idesc, accumulate);
                         for (int j = 1; j < ksteps; ++j) {
                             const uint32_t blk = j >> 2, st = j & 3;
                             umma_bf16(d_tmem, ad0 + blk * (C::kABlock >> 4) + 2 * st, bd0 + blk * (C::kBBlock >> 4) + 2 * st, idesc, 1u);
                         }
                         umma_commit(empty_bar + 8 * s);        // stage reusable once these MMAs have read it
                     }
+                    accumulate = 1u;
                     __syncwarp();
                     if (dbg && blockIdx.x == 0 && lane == 0 && g < 256) dbg[6 * 256 + g] = clock64();
                 }
@@ -340,6 +364,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
             mbar_wait(acc_full + 8 * ab, (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row = t * kTileM + q * 32 + lane;          // TMEM lane = tile row
+            // row of y this tile row is written to (class-sorted dgrad launches scatter back to canonical rows)
+            const int orow = (out_rows && row < n_out) ? __ldg(out_rows + row) : row;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * COUT;
 #pragma unroll
             for (int n0 = 0; n0 < COUT; n0 += 16) {
@@ -354,7 +380,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
 #pragma unroll
                 for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + n0 + j) : 0.f);
                 if (row < n_out) {
-                    float4 *dst = (float4 *)(y + (size_t)row * COUT + n0);
+                    float4 *dst = (float4 *)(y + (size_t)orow * COUT + n0);
 #pragma unroll
                     for (int qq = 0; qq < 4; ++qq) dst[qq] = make_float4(o[4 * qq], o[4 * qq + 1], o[4 * qq + 2], o[4 * qq + 3]);
                 }
@@ -436,12 +462,41 @@ __global__ void weight_to_kmajor_bf16_kernel(const float *__restrict__ w, int kv
     }
 }
 
+// masks[t] bit k = some row of tile t (128 rows) has a neighbour under offset k.  One warp per tile.
+__global__ void table_tile_masks_kernel(const int *__restrict__ nbr, int n_out, int kvol, int num_tiles, uint32_t *__restrict__ masks) {
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (t >= num_tiles) return;
+    const int row0 = t * kTileM;
+    uint32_t m = 0;
+    for (int k = 0; k < kvol; ++k) {
+        const int *src = nbr + (size_t)k * n_out + row0;
+        int any = 0;
+#pragma unroll
+        for (int j = 0; j < kTileM / 32; ++j) {
+            const int r = lane + 32 * j;
+            if (row0 + r < n_out) any |= (__ldg(src + r) >= 0);
+        }
+        if (__any_sync(0xffffffffu, any)) m |= 1u << k;
+    }
+    if (lane == 0) masks[t] = m;
+}
+
 }  // namespace
+
+extern "C" int toda_table_tile_masks(const int32_t *nbr, int n_out, int kvol, uint32_t *masks, void *stream) {
+    TODA_CHECK_ARG(n_out >= 0 && kvol > 0 && kvol <= 32, "table_tile_masks: bad sizes n_out=%d kvol=%d", n_out, kvol);
+    if (n_out == 0) return TODA_OK;
+    TODA_CHECK_ARG(nbr && masks, "table_tile_masks: null pointer");
+    const int num_tiles = ceil_div(n_out, kTileM);
+    table_tile_masks_kernel<<<ceil_div(num_tiles * 32, 256), 256, 0, (cudaStream_t)stream>>>(nbr, n_out, kvol, num_tiles, masks);
+    TODA_LAUNCH_OK();
+    return TODA_OK;
+}
 
 static inline int pad16(int c) { return c < 16 ? 16 : c; }
 
 int conv_tma_fwd(const void *xb, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const void *wb, int cout,
-                 const float *bias, float *y, double *bn_sums, cudaStream_t st);
+                 const float *bias, float *y, const int32_t *out_rows, double *bn_sums, cudaStream_t st);
 // 2-D bf16 row-major tensor map [rows][cols] with box [box_rows][box_cols], swizzle by box row bytes (conv_tma.cu)
 int conv_tma_make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols);
 
@@ -460,7 +515,8 @@ size_t conv_tc_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol) {
 }
 
 int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *w,
-                int cout, const float *bias, float *y, double *bn_sums, void *workspace, size_t workspace_bytes,
+                int cout, const float *bias, float *y, const int32_t *out_rows, const uint32_t *tile_masks, double *bn_sums,
+                void *workspace, size_t workspace_bytes,
                 cudaStream_t st) {
     size_t need = conv_tc_fwd_workspace_bytes(n_in, cin, cout, kvol);
     if (!workspace || workspace_bytes < need) {
@@ -493,7 +549,7 @@ int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int
     static int feed = -1;
     if (feed < 0) { const char *e = getenv("TODA_TC_FEED"); feed = !e ? 2 : (e[0] == 'c' ? 0 : 1); }
     if (feed == 1 || (feed == 2 && cin == 128 && cout == 128))
-        return conv_tma_fwd(xb, n_in, cin, nbr, n_out, kvol, wb, cout, bias, y, bn_sums, st);
+        return conv_tma_fwd(xb, n_in, cin, nbr, n_out, kvol, wb, cout, bias, y, out_rows, bn_sums, st);
     int num_tiles = ceil_div(n_out, kTileM);
     int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;   // persistent: one CTA per SM walks the tiles
     CUtensorMap map_w;
@@ -509,7 +565,7 @@ int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int
             TODA_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_kernel<CI, CO, KB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
             attr_set = true;                                                                                                 \
         }                                                                                                                    \
-        conv_tc_fwd_kernel<CI, CO, KB_><<<grid, kFwdThreads, smem, st>>>(xb, nbr, n_out, kvol, map_w, bias, y, bn_sums, num_tiles, g_dbg_timeline); \
+        conv_tc_fwd_kernel<CI, CO, KB_><<<grid, kFwdThreads, smem, st>>>(xb, nbr, n_out, kvol, map_w, bias, y, out_rows, tile_masks, bn_sums, num_tiles, g_dbg_timeline); \
     } while (0)
 #define LAUNCH_TC(CI, CO)                                                                                                    \
     do {                                                                                                                     \

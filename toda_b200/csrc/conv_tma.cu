@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_fwd_kernel(const __grid_
                                                                    const __grid_constant__ CUtensorMap map_w,
                                                                    const int *__restrict__ nbr, int n_in, int n_out, int kvol,
                                                                    const float *__restrict__ bias, float *__restrict__ y,
+                                                                   const int *__restrict__ out_rows /* optional */,
                                                                    double *__restrict__ bn_sums, int num_tiles) {
     using C = Cfg<CIN, COUT>;
     constexpr int S = C::kStages;
@@ -253,6 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_fwd_kernel(const __grid_
             mbar_wait(acc_full + 8 * ab, (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row = t * kTileM + q * 32 + lane;          // TMEM lane = tile row
+            const int orow = (out_rows && row < n_out) ? __ldg(out_rows + row) : row;    // see conv_tc.cu
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * COUT;
 #pragma unroll
             for (int n0 = 0; n0 < COUT; n0 += 16) {
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_fwd_kernel(const __grid_
 #pragma unroll
                 for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + n0 + j) : 0.f);
                 if (row < n_out) {
-                    float4 *dst = (float4 *)(y + (size_t)row * COUT + n0);
+                    float4 *dst = (float4 *)(y + (size_t)orow * COUT + n0);
 #pragma unroll
                     for (int qq = 0; qq < 4; ++qq) dst[qq] = make_float4(o[4 * qq], o[4 * qq + 1], o[4 * qq + 2], o[4 * qq + 3]);
                 }
@@ -350,7 +352,7 @@ int make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint
 
 template <int CIN, int COUT>
 int launch(const __nv_bfloat16 *xb, int n_in, const int32_t *nbr, int n_out, int kvol, const __nv_bfloat16 *wb, const float *bias,
-           float *y, double *bn_sums, cudaStream_t st) {
+           float *y, const int32_t *out_rows, double *bn_sums, cudaStream_t st) {
     using C = Cfg<CIN, COUT>;
     CUtensorMap mx, mw;
     if (int rc = make_map(&mx, xb, (uint64_t)n_in, CIN, 1, C::kRowElems)) return rc;              // gather4: box = one row
@@ -362,7 +364,7 @@ int launch(const __nv_bfloat16 *xb, int n_in, const int32_t *nbr, int n_out, int
         TODA_CUDA_OK(cudaFuncSetAttribute(conv_tma_fwd_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
         attr_set = true;
     }
-    conv_tma_fwd_kernel<CIN, COUT><<<grid, kThreads, C::kSmem, st>>>(mx, mw, nbr, n_in, n_out, kvol, bias, y, bn_sums, num_tiles);
+    conv_tma_fwd_kernel<CIN, COUT><<<grid, kThreads, C::kSmem, st>>>(mx, mw, nbr, n_in, n_out, kvol, bias, y, out_rows, bn_sums, num_tiles);
     TODA_LAUNCH_OK();
     return TODA_OK;
 }
@@ -375,14 +377,14 @@ int conv_tma_make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t c
 
 // xb: bf16 [n_in][cin], wb: bf16 [cout][kvol*cin]; cin, cout in {16,32,64,128}
 int conv_tma_fwd(const void *xb, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const void *wb, int cout,
-                 const float *bias, float *y, double *bn_sums, cudaStream_t st) {
+                 const float *bias, float *y, const int32_t *out_rows, double *bn_sums, cudaStream_t st) {
     const __nv_bfloat16 *x = (const __nv_bfloat16 *)xb, *w = (const __nv_bfloat16 *)wb;
 #define CASE_CO(CI)                                                                                    \
     switch (cout) {                                                                                    \
-        case 16: return launch<CI, 16>(x, n_in, nbr, n_out, kvol, w, bias, y, bn_sums, st);                     \
-        case 32: return launch<CI, 32>(x, n_in, nbr, n_out, kvol, w, bias, y, bn_sums, st);                     \
-        case 64: return launch<CI, 64>(x, n_in, nbr, n_out, kvol, w, bias, y, bn_sums, st);                     \
-        case 128: return launch<CI, 128>(x, n_in, nbr, n_out, kvol, w, bias, y, bn_sums, st);                   \
+        case 16: return launch<CI, 16>(x, n_in, nbr, n_out, kvol, w, bias, y, out_rows, bn_sums, st);                     \
+        case 32: return launch<CI, 32>(x, n_in, nbr, n_out, kvol, w, bias, y, out_rows, bn_sums, st);                     \
+        case 64: return launch<CI, 64>(x, n_in, nbr, n_out, kvol, w, bias, y, out_rows, bn_sums, st);                     \
+        case 128: return launch<CI, 128>(x, n_in, nbr, n_out, kvol, w, bias, y, out_rows, bn_sums, st);                   \
     }                                                                                                  \
     break;
     switch (cin) {

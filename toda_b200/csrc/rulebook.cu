@@ -138,3 +138,124 @@ extern "C" int toda_rulebook_sparse(const void *index_in, int iD, int iH, int iW
     }
     return TODA_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Parity order of the input rows of a strided convolution (used by its dgrad, see toda_spconv_fwd's out_rows):
+// class(row) = (((z+pz) % sz) * sy + (y+py) % sy) * sx + (x+px) % sx; rows sorted by class, canonical order kept inside a
+// class (stable counting sort, deterministic).  Two launches over 1024-row tiles: per-tile class histograms, then
+// class bases (sum over all tiles, tiny) + per-row ranks by warp ballots.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kPoThreads = 256, kPoTile = 1024, kPoMaxClasses = 8;
+
+struct ParityGeom { int s[3], p[3]; };
+
+__device__ __forceinline__ int parity_class(const int32_t *__restrict__ coords, int row, const ParityGeom &g) {
+    const int4 c = __ldg((const int4 *)coords + row);          // (b, z, y, x)
+    return (((c.y + g.p[0]) % g.s[0]) * g.s[1] + (c.z + g.p[1]) % g.s[1]) * g.s[2] + (c.w + g.p[2]) % g.s[2];
+}
+
+__global__ void __launch_bounds__(kPoThreads) parity_count_kernel(const int32_t *__restrict__ coords, int n, ParityGeom g,
+                                                                  int nclasses, int *__restrict__ tile_counts) {
+    __shared__ int cnt[kPoMaxClasses];
+    if (threadIdx.x < kPoMaxClasses) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int tile0 = blockIdx.x * kPoTile, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < kPoTile / kPoThreads; ++j) {
+        const int row = tile0 + j * kPoThreads + threadIdx.x;
+        const int c = row < n ? parity_class(coords, row, g) : -1;
+        for (int q = 0; q < nclasses; ++q) {
+            const uint32_t b = __ballot_sync(0xffffffffu, c == q);
+            if (lane == 0 && b) atomicAdd(&cnt[q], __popc(b));      // shared-memory integer adds: order-independent
+        }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nclasses) tile_counts[blockIdx.x * kPoMaxClasses + threadIdx.x] = cnt[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kPoThreads) parity_scatter_kernel(const int32_t *__restrict__ coords, int n, ParityGeom g,
+                                                                    int nclasses, const int *__restrict__ tile_counts,
+                                                                    int num_tiles, int32_t *__restrict__ order,
+                                                                    int32_t *__restrict__ pos_of_row) {
+    __shared__ int before[kPoMaxClasses], total[kPoMaxClasses], base[kPoMaxClasses];
+    __shared__ int slice_cnt[kPoTile / 32][kPoMaxClasses];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // per class: rows in earlier tiles, rows in all tiles (one warp per class, lanes stride over the tiles)
+    if (warp < nclasses) {
+        int b = 0, t = 0;
+        for (int i = lane; i < num_tiles; i += 32) {
+            const int v = tile_counts[i * kPoMaxClasses + warp];
+            t += v;
+            if (i < (int)blockIdx.x) b += v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { b += __shfl_xor_sync(0xffffffffu, b, o); t += __shfl_xor_sync(0xffffffffu, t, o); }
+        if (lane == 0) { before[warp] = b; total[warp] = t; }
+    }
+    const int tile0 = blockIdx.x * kPoTile;
+    int cls[kPoTile / kPoThreads], rank[kPoTile / kPoThreads];
+#pragma unroll
+    for (int j = 0; j < kPoTile / kPoThreads; ++j) {
+        const int row = tile0 + j * kPoThreads + threadIdx.x;
+        const int c = row < n ? parity_class(coords, row, g) : -1;
+        cls[j] = c;
+        rank[j] = 0;
+        const int slice = j * (kPoThreads / 32) + warp;          // slices are in row order
+        for (int q = 0; q < nclasses; ++q) {
+            const uint32_t b = __ballot_sync(0xffffffffu, c == q);
+            if (c == q) rank[j] = __popc(b & ((1u << lane) - 1u));
+            if (lane == 0) slice_cnt[slice][q] = __popc(b);
+        }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nclasses) {
+        const int q = threadIdx.x;
+        int start = 0;
+        for (int c = 0; c < q; ++c) start += total[c];
+        base[q] = start + before[q];
+        int run = 0;                                              // exclusive prefix over the tile's 32 slices
+        for (int s = 0; s < kPoTile / 32; ++s) { const int v = slice_cnt[s][q]; slice_cnt[s][q] = run; run += v; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kPoTile / kPoThreads; ++j) {
+        const int row = tile0 + j * kPoThreads + threadIdx.x;
+        if (row >= n) continue;
+        const int slice = j * (kPoThreads / 32) + warp;
+        const int pos = base[cls[j]] + slice_cnt[slice][cls[j]] + rank[j];
+        order[pos] = row;
+        if (pos_of_row) pos_of_row[row] = pos;
+    }
+}
+
+}  // namespace
+
+extern "C" size_t toda_parity_order_workspace_bytes(int n) {
+    return n < 0 ? 0 : (size_t)ceil_div(n > 0 ? n : 1, kPoTile) * kPoMaxClasses * sizeof(int) + 256;
+}
+
+extern "C" int toda_parity_order(const int32_t *coords, int n, const int *stride_host, const int *pad_host, int32_t *order,
+                                 int32_t *pos_of_row, void *workspace, size_t workspace_bytes, void *stream) {
+    TODA_CHECK_ARG(n >= 0 && stride_host && pad_host, "parity_order: bad arguments");
+    ParityGeom g;
+    int nclasses = 1;
+    for (int a = 0; a < 3; ++a) {
+        g.s[a] = stride_host[a];
+        g.p[a] = pad_host[a];
+        TODA_CHECK_ARG(g.s[a] >= 1 && g.p[a] >= 0, "parity_order: bad stride / padding");
+        nclasses *= g.s[a];
+    }
+    TODA_CHECK_ARG(nclasses <= kPoMaxClasses, "parity_order: %d parity classes > %d", nclasses, kPoMaxClasses);
+    if (n == 0) return TODA_OK;
+    TODA_CHECK_ARG(coords && order && workspace, "parity_order: null pointer");
+    if (workspace_bytes < toda_parity_order_workspace_bytes(n)) { toda_set_error("parity_order: workspace too small"); return TODA_ERR_WORKSPACE; }
+    const int tiles = ceil_div(n, kPoTile);
+    cudaStream_t st = (cudaStream_t)stream;
+    parity_count_kernel<<<tiles, kPoThreads, 0, st>>>(coords, n, g, nclasses, (int *)workspace);
+    TODA_LAUNCH_OK();
+    parity_scatter_kernel<<<tiles, kPoThreads, 0, st>>>(coords, n, g, nclasses, (const int *)workspace, tiles, order, pos_of_row);
+    TODA_LAUNCH_OK();
+    return TODA_OK;
+}

@@ -365,6 +365,10 @@ class Rulebook:
     out_coords: torch.Tensor          # (n_out,4) canonical
     nbr_fwd: torch.Tensor             # (kvol, n_out): input row per output row
     nbr_bwd: Optional[torch.Tensor]   # (kvol, n_in): output row per input row (None for SubM: mirrored nbr_fwd)
+    # strided convs, for dgrad: input rows sorted by parity class (int32 (n_in,)) and nbr_bwd with its columns in that order
+    dgrad_order: Optional[torch.Tensor] = None
+    nbr_bwd_sorted: Optional[torch.Tensor] = None
+    dgrad_tile_masks: Optional[torch.Tensor] = None   # per 128-row tile of nbr_bwd_sorted: which offsets hold a neighbour
 
     @property
     def kvol(self):
@@ -413,7 +417,41 @@ def rulebook_sparse(index_in: OccupancyIndex, ksize, stride, padding, tag):
     _count(2)
     rb = Rulebook(False, list(ksize), list(stride), list(padding), index_in.shape, out_shape, n_in, n_out, out_coords,
                   nbr_fwd, nbr_bwd)
+    rb.dgrad_order, rb.nbr_bwd_sorted = _dgrad_parity_order(index_in.coords, nbr_bwd, stride, padding)
+    if rb.dgrad_order is not None:
+        rb.dgrad_tile_masks = table_tile_masks(rb.nbr_bwd_sorted)
     return rb, index_out
+
+
+def table_tile_masks(nbr):
+    """uint32 per 128-row tile of a neighbour table: bit k = some row of the tile has a neighbour under offset k."""
+    kvol, n = nbr.shape
+    masks = torch.empty(((n + 127) // 128,), dtype=torch.int32, device=nbr.device)
+    _C.check(_C.lib().toda_table_tile_masks(_p(nbr), n, kvol, _p(masks), _stream()), "toda_table_tile_masks")
+    _count(1)
+    return masks
+
+
+def _dgrad_parity_order(in_coords, nbr_bwd, stride, padding):
+    """Input rows of a strided conv sorted by parity class ((z+pz) % sz, (y+py) % sy, (x+px) % sx), canonical order kept
+    inside a class, and the input-stationary table with its columns in that order.
+
+    out = (in + pad - k) / stride is integral only for k = (in + pad) mod stride (+ multiples of stride), so an input voxel
+    can be reached through 1..8 of the 27 offsets of a k3 s2 conv only: in canonical order every 128-row tile mixes all
+    classes and the dense [27] table is ~85 % structural padding, in class order most K blocks of a tile are empty and the
+    tensor-core kernel skips them (per-tile offset masks, see toda_spconv_fwd's out_rows)."""
+    if all(s == 1 for s in stride) or in_coords.shape[0] == 0:
+        return None, None
+    if stride[0] * stride[1] * stride[2] > 8:
+        return None, None
+    n = in_coords.shape[0]
+    L = _C.lib()
+    ws = _workspace("parity", L.toda_parity_order_workspace_bytes(n), in_coords.device)
+    order = torch.empty((n,), dtype=torch.int32, device=in_coords.device)
+    _C.check(L.toda_parity_order(_p(in_coords), n, _C.ints(stride), _C.ints(padding), _p(order), None, _p(ws), ws.numel(),
+                                 _stream()), "toda_parity_order")
+    _count(2)
+    return order, nbr_bwd.index_select(1, order).contiguous()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -448,15 +486,17 @@ def _bf16_shadow_of(t):
     return None
 
 
-def _conv_call(x, xb, cin, nbr, n_out, kvol, w, cout, bias, precision, what="conv_fwd", rb=None, bn_sums=None):
-    y = torch.empty((n_out, cout), dtype=torch.float32, device=x.device)
+def _conv_call(x, xb, cin, nbr, n_out, kvol, w, cout, bias, precision, what="conv_fwd", rb=None, bn_sums=None, y=None,
+               out_rows=None, tile_masks=None):
+    if y is None:
+        y = torch.empty((n_out, cout), dtype=torch.float32, device=x.device)
     L = _C.lib()
     ws_bytes = L.toda_spconv_fwd_workspace_bytes(x.shape[0], cin, cout, kvol, precision)
     ws = _workspace("conv", ws_bytes, x.device) if ws_bytes else None
     with _timed(what, n_in=x.shape[0], n_out=n_out, cin=cin, cout=cout, kvol=kvol, precision=precision, rb=id(rb)):
         _C.check(L.toda_spconv_fwd(_p(x), _p(xb), x.shape[0], cin, _p(nbr), n_out, kvol, _p(w), cout, _p(bias), _p(y),
-                                   _p(bn_sums), precision, _p(ws), ws.numel() if ws is not None else 0, _stream()),
-                 "toda_spconv_fwd")
+                                   _p(out_rows), _p(tile_masks), _p(bn_sums), precision, _p(ws), ws.numel() if ws is not None else 0,
+                                   _stream()), "toda_spconv_fwd")
     _count(1)
     return y
 
@@ -498,8 +538,14 @@ class _SparseConv(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             # dgrad = the same gather-GEMM on the input-stationary table with transposed weights
             wt = _repack(weight, True, rb.subm)
-            table = rb.nbr_fwd if rb.subm else rb.nbr_bwd
-            dx = _conv_call(dy, dyb, cout, table, rb.n_in, rb.kvol, wt, cin, None, precision, "conv_dgrad", rb)
+            if rb.subm:
+                dx = _conv_call(dy, dyb, cout, rb.nbr_fwd, rb.n_in, rb.kvol, wt, cin, None, precision, "conv_dgrad", rb)
+            elif rb.dgrad_order is None:
+                dx = _conv_call(dy, dyb, cout, rb.nbr_bwd, rb.n_in, rb.kvol, wt, cin, None, precision, "conv_dgrad", rb)
+            else:
+                # strided conv: rows in parity-class order (empty K blocks are skipped), written back to canonical rows
+                dx = _conv_call(dy, dyb, cout, rb.nbr_bwd_sorted, rb.n_in, rb.kvol, wt, cin, None, precision, "conv_dgrad",
+                                rb, out_rows=rb.dgrad_order, tile_masks=rb.dgrad_tile_masks)
         if ctx.needs_input_grad[2]:
             dw = torch.empty_like(weight)
             ws_bytes = L.toda_spconv_wgrad_workspace_bytes(rb.n_in, rb.n_out, rb.kvol, cin, cout, precision)

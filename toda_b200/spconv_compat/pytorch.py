@@ -243,6 +243,8 @@ class GeometryPlan:
                 out.append(rb.nbr_bwd)
             if index_out.frame_counts is not None:
                 out.append(index_out.frame_counts)
+            if rb.dgrad_order is not None:
+                out += [rb.dgrad_order, rb.nbr_bwd_sorted, rb.dgrad_tile_masks]
         return [t for t in out if t is not None]
 
     def sparse_tensor(self, features, features_bf16=None):
