@@ -501,22 +501,57 @@ def _conv_call(x, xb, cin, nbr, n_out, kvol, w, cout, bias, precision, what="con
     return y
 
 
+def _conv_forward_impl(x, x_bf16, weight, bias, rb, precision, want_stats):
+    """-> (y, sums, x, weight, x_bf16): the conv output, the fused BN sums (or None) and the tensors backward needs."""
+    x = _need(x.contiguous(), torch.float32, "features")
+    weight = _need(weight.contiguous(), torch.float32, "weight")
+    cout, cin = weight.shape[0], weight.shape[4]
+    assert x.shape == (rb.n_in, cin), (x.shape, rb.n_in, cin)
+    if x_bf16 is not None and (precision != CONV_BF16 or x_bf16.shape != x.shape or x_bf16.dtype != torch.bfloat16
+                               or not x_bf16.is_contiguous()):
+        x_bf16 = None
+    w = _repack(weight, False, False)
+    b = bias.contiguous() if bias is not None else None
+    sums = None
+    if want_stats and rb.n_out > 0 and _C.lib().toda_spconv_uses_tensor_cores(cin, cout, rb.kvol, precision):
+        sums = torch.empty((2 * cout,), dtype=torch.float64, device=x.device)
+    y = _conv_call(x, x_bf16, cin, rb.nbr_fwd, rb.n_out, rb.kvol, w, cout, b, precision, "conv_fwd", rb, sums)
+    return y, sums, x, weight, x_bf16
+
+
+def _conv_backward_impl(dy, dyb, x, weight, xb, rb, precision, need_dx, need_dw, need_db):
+    cout, cin = weight.shape[0], weight.shape[4]
+    L = _C.lib()
+    dx = dw = db = None
+    if need_dx:
+        # dgrad = the same gather-GEMM on the input-stationary table with transposed weights
+        wt = _repack(weight, True, rb.subm)
+        if rb.subm:
+            dx = _conv_call(dy, dyb, cout, rb.nbr_fwd, rb.n_in, rb.kvol, wt, cin, None, precision, "conv_dgrad", rb)
+        elif rb.dgrad_order is None:
+            dx = _conv_call(dy, dyb, cout, rb.nbr_bwd, rb.n_in, rb.kvol, wt, cin, None, precision, "conv_dgrad", rb)
+        else:
+            # strided conv: rows in parity-class order (empty K blocks are skipped), written back to canonical rows
+            dx = _conv_call(dy, dyb, cout, rb.nbr_bwd_sorted, rb.n_in, rb.kvol, wt, cin, None, precision, "conv_dgrad",
+                            rb, out_rows=rb.dgrad_order, tile_masks=rb.dgrad_tile_masks)
+    if need_dw:
+        dw = torch.empty_like(weight)
+        ws_bytes = L.toda_spconv_wgrad_workspace_bytes(rb.n_in, rb.n_out, rb.kvol, cin, cout, precision)
+        ws = _workspace("wgrad", ws_bytes, dy.device)
+        with _timed("conv_wgrad", n_in=rb.n_in, n_out=rb.n_out, cin=cin, cout=cout, kvol=rb.kvol, precision=precision,
+                    rb=id(rb)):
+            _C.check(L.toda_spconv_wgrad(_p(x), _p(xb), rb.n_in, cin, _p(rb.nbr_fwd), rb.n_out, rb.kvol, _p(dy), _p(dyb),
+                                         cout, _p(dw), _p(ws), ws.numel(), precision, _stream()), "toda_spconv_wgrad")
+        _count(2)
+    if need_db:
+        db = col_sum(dy)
+    return dx, dw, db
+
+
 class _SparseConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, x_bf16, weight, bias, rb: Rulebook, precision, want_stats):
-        x = _need(x.contiguous(), torch.float32, "features")
-        weight = _need(weight.contiguous(), torch.float32, "weight")
-        cout, cin = weight.shape[0], weight.shape[4]
-        assert x.shape == (rb.n_in, cin), (x.shape, rb.n_in, cin)
-        if x_bf16 is not None and (precision != CONV_BF16 or x_bf16.shape != x.shape or x_bf16.dtype != torch.bfloat16
-                                   or not x_bf16.is_contiguous()):
-            x_bf16 = None
-        w = _repack(weight, False, False)
-        b = bias.contiguous() if bias is not None else None
-        sums = None
-        if want_stats and rb.n_out > 0 and _C.lib().toda_spconv_uses_tensor_cores(cin, cout, rb.kvol, precision):
-            sums = torch.empty((2 * cout,), dtype=torch.float64, device=x.device)
-        y = _conv_call(x, x_bf16, cin, rb.nbr_fwd, rb.n_out, rb.kvol, w, cout, b, precision, "conv_fwd", rb, sums)
+        y, sums, x, weight, x_bf16 = _conv_forward_impl(x, x_bf16, weight, bias, rb, precision, want_stats)
         ctx.save_for_backward(x, weight, x_bf16)
         ctx.set_materialize_grads(False)      # no zero tensors for the non-differentiable outputs
         ctx.rb, ctx.precision, ctx.has_bias = rb, precision, bias is not None
@@ -529,34 +564,9 @@ class _SparseConv(torch.autograd.Function):
         if dy is None:
             return (None,) * 7
         x, weight, xb = ctx.saved_tensors
-        rb, precision = ctx.rb, ctx.precision
-        cout, cin = weight.shape[0], weight.shape[4]
-        dyb = _bf16_shadow_of(dy) if (precision == CONV_BF16 and dy.is_contiguous()) else None
-        dy = dy.contiguous()
-        L = _C.lib()
-        dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            # dgrad = the same gather-GEMM on the input-stationary table with transposed weights
-            wt = _repack(weight, True, rb.subm)
-            if rb.subm:
-                dx = _conv_call(dy, dyb, cout, rb.nbr_fwd, rb.n_in, rb.kvol, wt, cin, None, precision, "conv_dgrad", rb)
-            elif rb.dgrad_order is None:
-                dx = _conv_call(dy, dyb, cout, rb.nbr_bwd, rb.n_in, rb.kvol, wt, cin, None, precision, "conv_dgrad", rb)
-            else:
-                # strided conv: rows in parity-class order (empty K blocks are skipped), written back to canonical rows
-                dx = _conv_call(dy, dyb, cout, rb.nbr_bwd_sorted, rb.n_in, rb.kvol, wt, cin, None, precision, "conv_dgrad",
-                                rb, out_rows=rb.dgrad_order, tile_masks=rb.dgrad_tile_masks)
-        if ctx.needs_input_grad[2]:
-            dw = torch.empty_like(weight)
-            ws_bytes = L.toda_spconv_wgrad_workspace_bytes(rb.n_in, rb.n_out, rb.kvol, cin, cout, precision)
-            ws = _workspace("wgrad", ws_bytes, dy.device)
-            with _timed("conv_wgrad", n_in=rb.n_in, n_out=rb.n_out, cin=cin, cout=cout, kvol=rb.kvol, precision=precision,
-                        rb=id(rb)):
-                _C.check(L.toda_spconv_wgrad(_p(x), _p(xb), rb.n_in, cin, _p(rb.nbr_fwd), rb.n_out, rb.kvol, _p(dy), _p(dyb),
-                                             cout, _p(dw), _p(ws), ws.numel(), precision, _stream()), "toda_spconv_wgrad")
-            _count(2)
-        if ctx.has_bias and ctx.needs_input_grad[3]:
-            db = col_sum(dy)
+        dyb = _bf16_shadow_of(dy) if (ctx.precision == CONV_BF16 and dy.is_contiguous()) else None
+        dx, dw, db = _conv_backward_impl(dy.contiguous(), dyb, x, weight, xb, ctx.rb, ctx.precision, ctx.needs_input_grad[0],
+                                         ctx.needs_input_grad[2], ctx.has_bias and ctx.needs_input_grad[3])
         return dx, None, dw, db, None, None, None
 
 
@@ -580,44 +590,71 @@ def col_sum(t):
 # ------------------------------------------------------------------------------------------------
 # K8 BatchNorm + ReLU (+ residual)
 # ------------------------------------------------------------------------------------------------
+def _bn_forward_impl(y, gamma, beta, running_mean, running_var, eps, momentum, training, residual, relu, want_bf16, sums,
+                     need_grad):
+    """-> (a, a_bf16, y, mean, rstd)"""
+    y = _need(y.contiguous(), torch.float32, "bn input")
+    n, c = y.shape
+    dev = y.device
+    L = _C.lib()
+    scale = torch.empty((c,), dtype=torch.float32, device=dev)
+    shift = torch.empty_like(scale)
+    if training and sums is not None:
+        mean = torch.empty_like(scale)
+        rstd = torch.empty_like(scale)
+        _C.check(L.toda_bn_finalize_sums(_p(sums), n, c, _p(gamma), _p(beta), float(eps), float(momentum),
+                                         _p(running_mean), _p(running_var), _p(scale), _p(shift), _p(mean), _p(rstd),
+                                         _stream()), "toda_bn_finalize_sums")
+        _count(1)
+    elif training:
+        mean = torch.empty_like(scale)
+        rstd = torch.empty_like(scale)
+        ws = _workspace("bn", L.toda_bn_workspace_bytes(c), dev)
+        with _timed("bn_stats", n=n, c=c):
+            _C.check(L.toda_bn_stats(_p(y), n, c, _p(gamma), _p(beta), float(eps), float(momentum), _p(running_mean),
+                                     _p(running_var), _p(scale), _p(shift), _p(mean), _p(rstd), _p(ws), ws.numel(),
+                                     _stream()), "toda_bn_stats")
+        _count(2)
+    else:
+        _C.check(L.toda_bn_eval_coeffs(_p(gamma), _p(beta), _p(running_mean), _p(running_var), float(eps), c, _p(scale),
+                                       _p(shift), _stream()), "toda_bn_eval_coeffs")
+        _count(1)
+        mean = running_mean
+        rstd = torch.rsqrt(running_var + eps) if need_grad else None
+    res = residual.contiguous() if residual is not None else None
+    a = torch.empty_like(y)
+    ab = torch.empty(y.shape, dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    with _timed("bn_apply", n=n, c=c, residual=res is not None):
+        _C.check(L.toda_bn_apply(_p(y), n, c, _p(scale), _p(shift), _p(res), int(relu), _p(a), _p(ab), _stream()),
+                 "toda_bn_apply")
+    _count(1)
+    return a, ab, y, mean, rstd
+
+
+def _bn_backward_impl(da, y, a, gamma, mean, rstd, training, relu, has_res, want_bf16):
+    """-> (dy, dy_bf16, dresidual, dgamma, dbeta)"""
+    n, c = y.shape
+    da = da.contiguous()
+    L = _C.lib()
+    dy = torch.empty_like(y)
+    dyb = torch.empty(y.shape, dtype=torch.bfloat16, device=y.device) if want_bf16 else None
+    dres = torch.empty_like(y) if has_res else None
+    dgamma = torch.empty((c,), dtype=torch.float32, device=y.device)
+    dbeta = torch.empty_like(dgamma)
+    ws = _workspace("bn", L.toda_bn_workspace_bytes(c), y.device)
+    with _timed("bn_bwd", n=n, c=c, residual=has_res):
+        _C.check(L.toda_bn_bwd(_p(da), _p(a), _p(y), n, c, _p(gamma), _p(mean), _p(rstd), int(relu), int(training),
+                               _p(dy), _p(dyb), _p(dres), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _stream()),
+                 "toda_bn_bwd")
+    _count(3)
+    return dy, dyb, dres, dgamma, dbeta
+
+
 class _BNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y, gamma, beta, running_mean, running_var, eps, momentum, training, residual, relu, want_bf16, sums):
-        y = _need(y.contiguous(), torch.float32, "bn input")
-        n, c = y.shape
-        dev = y.device
-        L = _C.lib()
-        scale = torch.empty((c,), dtype=torch.float32, device=dev)
-        shift = torch.empty_like(scale)
-        ws = _workspace("bn", L.toda_bn_workspace_bytes(c), dev)
-        if training and sums is not None:
-            mean = torch.empty_like(scale)
-            rstd = torch.empty_like(scale)
-            _C.check(L.toda_bn_finalize_sums(_p(sums), n, c, _p(gamma), _p(beta), float(eps), float(momentum),
-                                             _p(running_mean), _p(running_var), _p(scale), _p(shift), _p(mean), _p(rstd),
-                                             _stream()), "toda_bn_finalize_sums")
-            _count(1)
-        elif training:
-            mean = torch.empty_like(scale)
-            rstd = torch.empty_like(scale)
-            with _timed("bn_stats", n=n, c=c):
-                _C.check(L.toda_bn_stats(_p(y), n, c, _p(gamma), _p(beta), float(eps), float(momentum), _p(running_mean),
-                                         _p(running_var), _p(scale), _p(shift), _p(mean), _p(rstd), _p(ws), ws.numel(),
-                                         _stream()), "toda_bn_stats")
-            _count(2)
-        else:
-            _C.check(L.toda_bn_eval_coeffs(_p(gamma), _p(beta), _p(running_mean), _p(running_var), float(eps), c, _p(scale),
-                                           _p(shift), _stream()), "toda_bn_eval_coeffs")
-            _count(1)
-            mean = running_mean
-            rstd = torch.rsqrt(running_var + eps) if y.requires_grad or gamma.requires_grad else None
-        res = residual.contiguous() if residual is not None else None
-        a = torch.empty_like(y)
-        ab = torch.empty(y.shape, dtype=torch.bfloat16, device=dev) if want_bf16 else None
-        with _timed("bn_apply", n=n, c=c, residual=res is not None):
-            _C.check(L.toda_bn_apply(_p(y), n, c, _p(scale), _p(shift), _p(res), int(relu), _p(a), _p(ab), _stream()),
-                     "toda_bn_apply")
-        _count(1)
+        a, ab, y, mean, rstd = _bn_forward_impl(y, gamma, beta, running_mean, running_var, eps, momentum, training, residual,
+                                                relu, want_bf16, sums, y.requires_grad or gamma.requires_grad)
         ctx.save_for_backward(y, a, gamma, mean, rstd)
         ctx.set_materialize_grads(False)      # the bf16 copy is non-differentiable: no zero tensor for it in backward
         ctx.cfg = (bool(training), bool(relu), residual is not None, bool(want_bf16))
@@ -631,23 +668,50 @@ class _BNAct(torch.autograd.Function):
             return (None,) * 12
         y, a, gamma, mean, rstd = ctx.saved_tensors
         training, relu, has_res, want_bf16 = ctx.cfg
-        n, c = y.shape
-        da = da.contiguous()
-        L = _C.lib()
-        dy = torch.empty_like(y)
-        dyb = torch.empty(y.shape, dtype=torch.bfloat16, device=y.device) if want_bf16 else None
-        dres = torch.empty_like(y) if has_res else None
-        dgamma = torch.empty((c,), dtype=torch.float32, device=y.device)
-        dbeta = torch.empty_like(dgamma)
-        ws = _workspace("bn", L.toda_bn_workspace_bytes(c), y.device)
-        with _timed("bn_bwd", n=n, c=c, residual=has_res):
-            _C.check(L.toda_bn_bwd(_p(da), _p(a), _p(y), n, c, _p(gamma), _p(mean), _p(rstd), int(relu), int(training),
-                                   _p(dy), _p(dyb), _p(dres), _p(dgamma), _p(dbeta), _p(ws), ws.numel(), _stream()),
-                     "toda_bn_bwd")
-        _count(3)
+        dy, dyb, dres, dgamma, dbeta = _bn_backward_impl(da, y, a, gamma, mean, rstd, training, relu, has_res, want_bf16)
         if dyb is not None:
             dy._toda_bf16 = (dyb, dy._version)     # picked up by the producing conv's backward (see _bf16_shadow_of)
         return dy, dgamma, dbeta, None, None, None, None, None, dres, None, None, None
+
+
+class _ConvBNAct(torch.autograd.Function):
+    """conv -> BatchNorm1d (+ residual) (+ ReLU) as ONE autograd node: half the Python / autograd-engine overhead per layer
+    of the two separate nodes, and the gradient between BN and conv (dy and its bf16 copy) never becomes a graph edge."""
+
+    @staticmethod
+    def forward(ctx, x, x_bf16, weight, bias, rb, precision, gamma, beta, running_mean, running_var, eps, momentum, training,
+                residual, relu, want_bf16):
+        y, sums, x, weight, x_bf16 = _conv_forward_impl(x, x_bf16, weight, bias, rb, precision, bool(training))
+        a, ab, y, mean, rstd = _bn_forward_impl(y, gamma, beta, running_mean, running_var, eps, momentum, training, residual,
+                                                relu, want_bf16, sums, True)
+        ctx.save_for_backward(x, weight, x_bf16, y, a, gamma, mean, rstd)
+        ctx.set_materialize_grads(False)
+        ctx.rb, ctx.precision, ctx.has_bias = rb, precision, bias is not None
+        ctx.cfg = (bool(training), bool(relu), residual is not None, bool(want_bf16))
+        if ab is not None:
+            ctx.mark_non_differentiable(ab)
+        return a, ab
+
+    @staticmethod
+    def backward(ctx, da, _dab=None):
+        if da is None:
+            return (None,) * 16
+        x, weight, xb, y, a, gamma, mean, rstd = ctx.saved_tensors
+        training, relu, has_res, want_bf16 = ctx.cfg
+        dy, dyb, dres, dgamma, dbeta = _bn_backward_impl(da, y, a, gamma, mean, rstd, training, relu, has_res,
+                                                         want_bf16 and ctx.precision == CONV_BF16)
+        dx, dw, db = _conv_backward_impl(dy, dyb, x, weight, xb, ctx.rb, ctx.precision, ctx.needs_input_grad[0],
+                                         ctx.needs_input_grad[2], ctx.has_bias and ctx.needs_input_grad[3])
+        return dx, None, dw, db, None, None, dgamma, dbeta, None, None, None, None, None, dres, None, None
+
+
+def conv_bn_act(x, weight, bias, rb, precision, bn: torch.nn.BatchNorm1d, residual=None, relu=True, x_bf16=None, want_bf16=False):
+    """Fused-node version of bn_act(sparse_conv(x, ...), bn, residual, relu).  -> (a, a_bf16 or None)"""
+    training = bn.training or bn.running_mean is None
+    if training and bn.running_mean is not None and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return _ConvBNAct.apply(x, x_bf16, weight, bias, rb, precision, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,
+                            bn.momentum, training, residual, relu, want_bf16)
 
 
 def bn_act(y, bn: torch.nn.BatchNorm1d, residual=None, relu=True, want_bf16=False, sums=None):

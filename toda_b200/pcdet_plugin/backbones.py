@@ -37,9 +37,14 @@ STAGES_RES = dict(
 )
 
 
-def make_backbones(sp, bn_act):
+def make_backbones(sp, bn_act, conv_bn_act=None):
     """sp: module with SparseConvTensor, SparseModule, SparseSequential, SubMConv3d, SparseConv3d.
-    bn_act(sparse_tensor, bn_module, residual_features, relu) -> sparse_tensor with the new features."""
+    bn_act(sparse_tensor, bn_module, residual_features, relu) -> sparse_tensor with the new features.
+    conv_bn_act(sparse_tensor, conv_module, bn_module, residual_features, relu) (optional): the same result as
+    bn_act(conv(x), ...) from one fused call."""
+    if conv_bn_act is None:
+        def conv_bn_act(x, conv, bn, residual, relu):
+            return bn_act(conv(x), bn, residual, relu)
     norm_fn = partial(nn.BatchNorm1d, eps=1e-3, momentum=0.01)
 
     class ConvBNReLU(sp.SparseSequential):
@@ -49,7 +54,7 @@ def make_backbones(sp, bn_act):
             super().__init__(conv, norm_fn(channels), nn.ReLU())
 
         def forward(self, x):
-            return bn_act(self[0](x), self[1], None, True)
+            return conv_bn_act(x, self[0], self[1], None, True)
 
     class SparseBasicBlock(sp.SparseModule):
         expansion = 1
@@ -65,8 +70,8 @@ def make_backbones(sp, bn_act):
         def forward(self, x):
             if hasattr(x, "canonical"):
                 x = x.canonical()      # the residual rows must line up with the conv outputs
-            out = bn_act(self.conv1(x), self.bn1, None, True)
-            return bn_act(self.conv2(out), self.bn2, x.features, True)
+            out = conv_bn_act(x, self.conv1, self.bn1, None, True)
+            return conv_bn_act(out, self.conv2, self.bn2, x.features, True)
 
     def build_stage(cin, spec):
         mods = []

@@ -106,6 +106,16 @@ def bn_act_tensor(x, bn, residual, relu):
     return x.replace_feature(ops.bn_act(x.features, bn, residual, relu))
 
 
+def conv_bn_act_tensor(x, conv, bn, residual, relu):
+    """bn_act_tensor(conv(x), bn, residual, relu) as one autograd node (ops.conv_bn_act): same kernels, half the host work."""
+    x = x.canonical()
+    rb, index_out = conv._rulebook(x)
+    bf16 = _precision == ops.CONV_BF16
+    a, ab = ops.conv_bn_act(x.features, conv.weight, conv.bias, rb, _precision, bn, residual, relu, x._features_bf16, bf16)
+    return SparseConvTensor(a, rb.out_coords, rb.out_shape, x.batch_size, x.grid, x.voxel_num, x.indice_dict, x.benchmark,
+                            index_out, ab)
+
+
 class SparseModule(nn.Module):
     """Marker base: SparseSequential hands the whole SparseConvTensor to these."""
     pass
@@ -137,7 +147,14 @@ class SparseSequential(SparseModule):
         i = 0
         while i < len(mods):
             m = mods[i]
-            if isinstance(m, SparseModule):
+            if (isinstance(m, SparseConvolution) and isinstance(x, SparseConvTensor) and i + 1 < len(mods)
+                    and type(mods[i + 1]) is nn.BatchNorm1d and mods[i + 1].affine and mods[i + 1].track_running_stats
+                    and x.features.is_cuda and x.indices.shape[0] > 0):
+                # conv + BatchNorm1d [+ ReLU]: one fused autograd node
+                relu = i + 2 < len(mods) and type(mods[i + 2]) is nn.ReLU
+                x = conv_bn_act_tensor(x, m, mods[i + 1], None, relu)
+                i += 3 if relu else 2
+            elif isinstance(m, SparseModule):
                 x = m(x)
                 i += 1
             elif isinstance(x, SparseConvTensor):
