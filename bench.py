@@ -30,6 +30,13 @@ def emit(line):
     os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
 
 
+# Row counts differ from batch to batch, so every step asks the caching allocator for slightly different sizes; with exact
+# sizes the freed blocks of one batch rarely fit the next, the pools fragment and torch falls back to cudaMalloc inside a
+# timed step (which stalls for as long as the GPU's queue: seen as single 40-70 ms steps).  Rounding request sizes to 1/8
+# power-of-two steps maps successive batches onto the same size classes.  (Standard PyTorch allocator option; must be
+# set before the first CUDA allocation.  INTEGRATION.md recommends the same for training runs.)
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "roundup_power2_divisions:8")
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -304,8 +311,11 @@ def run_ours(args, rank, world, local_rank):
         _, h = e2e_step(h, i)
     barrier()
     e0.record()
+    wall = [time.perf_counter()]
+    mark1 = len(trace) if trace is not None else 0
     for i in range(args.steps):
         _, h = e2e_step(h, i)
+        wall.append(time.perf_counter())
     torch.cuda.current_stream().wait_stream(pipe.stream)
     e1.record()
     barrier()
@@ -313,6 +323,11 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
+    if rank == 0:
+        print("per-step ms (e2e arm, host wall clock): " + " ".join("%.2f" % ((b - a) * 1e3) for a, b in zip(wall, wall[1:])),
+              file=sys.stderr)
+        if trace is not None:
+            print("host trace (ms) of the e2e steps: " + " ".join(str(t) for t in trace[mark1:]), file=sys.stderr)
     h2d = int(np.mean([p.numel() * 4 + o.numel() * 4 for p, o in hosts]))
     e2e = dict(value=world * FRAMES_PER_GPU * args.steps / (e2e_ms / 1e3), unit="frames/s", h2d_bytes_per_step=h2d,
                d2h_bytes_per_step=4 * 6, ms_per_step=e2e_ms / args.steps)
