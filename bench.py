@@ -267,7 +267,7 @@ def run_ours(args, rank, world, local_rank):
         gc.callbacks.append(gc_cb)
 
     h = front(*devs[0], False)
-    for i in range(POOL + args.warmup):       # every pooled batch once through the pipeline (side-stream pool), then W warm-up steps
+    for i in range(2 * POOL + args.warmup):   # every pooled batch twice through the pipeline (side-stream pool), then W warm-up steps
         loss, bd = back(h)
         h = front(*devs[(i + 1) % POOL], False)
     barrier()
@@ -281,7 +281,7 @@ def run_ours(args, rank, world, local_rank):
     marks[0].record()
     for i in range(args.steps):
         loss, bd = back(h)
-        h = front(*devs[(POOL + args.warmup + i + 1) % POOL], False)   # pre-staged, complete device tensors
+        h = front(*devs[(2 * POOL + args.warmup + i + 1) % POOL], False)   # pre-staged, complete device tensors
         marks[i + 1].record()
     torch.cuda.current_stream().wait_stream(pipe.stream)        # the last front belongs to the timed region too
     e1.record()

@@ -28,7 +28,7 @@ class _Handle:
 
 
 class InputPipeline:
-    def __init__(self, vfe, backbone, device, reserve_bytes=4 << 30):
+    def __init__(self, vfe, backbone, device, reserve_bytes=8 << 30):
         self.vfe, self.backbone = vfe, backbone
         self.device = torch.device(device)
         lo, hi = torch.cuda.Stream.priority_range()      # (lowest, highest): highest is the numerically smaller one
