@@ -1,7 +1,8 @@
 """sweep of point count x voxel size (one nuScenes-shaped frame resampled to N points).
 Per point: K1 voxelizer (GPU, CUDA events; CPU = the oracle's C loop on one core, the reference's per-worker behaviour),
 isolated SubMConv3d(64->64) and SparseConv3d(64->64, stride 2) forward on the resulting active set (bf16 tensor-core path).
-Prints a markdown table (committed as profiles/r01_sweep.md).  Development / measurement aid, not part of bench.py."""
+Prints a markdown table (committed as profiles/r01_sweep.md).  Lives under tests/ because its CPU column runs the oracle
+(test infrastructure); not collected by pytest, run as `python tests/sweep_config5.py` on a GPU box."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
