@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_fwd_kernel(const __grid_
                                                                    const int *__restrict__ nbr, int n_in, int n_out, int kvol,
                                                                    const float *__restrict__ bias, float *__restrict__ y,
                                                                    const int *__restrict__ out_rows /* optional */,
+                                                                   const uint32_t *__restrict__ tile_masks /* optional */,
                                                                    double *__restrict__ bn_sums, int num_tiles) {
     using C = Cfg<CIN, COUT>;
     constexpr int S = C::kStages;
@@ -153,6 +154,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_fwd_kernel(const __grid_
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nchunks = kvol * C::kChunksPerOffset;
+    // chunks of tile t that hold at least one real neighbour (see conv_tc.cu): bit c = chunk c; every role derives the
+    // same list from the tile's offset mask, an all-empty tile still walks chunk 0 so that its accumulator is defined
+    auto chunk_mask_of = [&](int t) -> unsigned long long {
+        if (!tile_masks) return nchunks >= 64 ? ~0ull : ((1ull << nchunks) - 1ull);
+        const uint32_t om = __ldg(tile_masks + t);
+        unsigned long long cm = 0ull;
+        for (int c = 0; c < nchunks; ++c)
+            if ((om >> (c / C::kChunksPerOffset)) & 1u) cm |= 1ull << c;
+        return cm ? cm : 1ull;
+    };
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
@@ -184,13 +195,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_fwd_kernel(const __grid_
         // ------------------------------------------------------------------ producers: warp w owns chunks g = w (mod 4)
         int it = 0;
         int g0 = 0;                       // global index of this tile's first chunk
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it, g0 += nchunks) {
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int ib = it & 1;
             mbar_wait(idx_full + 8 * ib, (it >> 1) & 1);
             const uint32_t idx_tile = idx_base + ib * kIdxBytes + 16 * lane;     // rows 4*lane .. 4*lane+3 of every offset
-            int c = (warp - g0 % kProdWarps + kProdWarps) % kProdWarps;          // first chunk of this tile owned by the warp
-            for (; c < nchunks; c += kProdWarps) {
-                const int g = g0 + c;
+            const unsigned long long cm0 = chunk_mask_of(t);
+            int g = g0;
+            for (unsigned long long cm = cm0; cm; cm &= cm - 1, ++g) {
+                if (g % kProdWarps != warp) continue;                            // chunks are dealt round-robin to the warps
+                const int c = __ffsll((long long)cm) - 1;
                 const int s = g % S, use = g / S;
                 if (use > 0) mbar_wait(empty_bar + 8 * s, (use - 1) & 1);
                 const uint32_t a_tile = base + s * C::kStage, b_tile = a_tile + C::kABytes;
@@ -208,6 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_fwd_kernel(const __grid_
                 __syncwarp();
                 tma_gather4(a_tile + lane * 4 * C::kRowBytes, &map_x, col, r0, r1, r2, r3, full_bar + 8 * s);
             }
+            g0 = g;
             __syncwarp();
             if (lane == 0) mbar_arrive(idx_empty + 8 * ib);   // this warp is done with the tile's table slice
         }
@@ -221,7 +235,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_fwd_kernel(const __grid_
                 const int ab = it & 1, ause = it >> 1;
                 if (ause > 0) mbar_wait(acc_empty + 8 * ab, (ause - 1) & 1);
                 const uint32_t d_tmem = tmem_base + ab * COUT;
-                for (int c = 0; c < nchunks; ++c, ++g) {
+                uint32_t accumulate = 0;
+                for (unsigned long long cm = chunk_mask_of(t); cm; cm &= cm - 1, ++g) {
                     const int s = g % S, use = g / S;
                     if (!ready) mbar_wait(full_bar + 8 * s, use & 1);
                     ready = mbar_test(full_bar + 8 * ((g + 1) % S), ((g + 1) / S) & 1);   // look one stage ahead
@@ -232,10 +247,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_fwd_kernel(const __grid_
                         for (int j = 0; j < C::kKSteps; ++j) {
                             uint64_t ad = make_desc_k(a_tile + j * 32, C::kSBO, C::kLayoutType);
                             uint64_t bd = make_desc_k(b_tile + j * 32, C::kSBO, C::kLayoutType);
-                            umma_bf16(d_tmem, ad, bd, idesc, (c | j) != 0);
+                            umma_bf16(d_tmem, ad, bd, idesc, accumulate | (uint32_t)(j != 0));
                         }
                         umma_commit(empty_bar + 8 * s);
                     }
+                    accumulate = 1u;
                     __syncwarp();
                 }
                 if (elect_one()) umma_commit(acc_full + 8 * ab);
@@ -352,7 +368,7 @@ int make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint
 
 template <int CIN, int COUT>
 int launch(const __nv_bfloat16 *xb, int n_in, const int32_t *nbr, int n_out, int kvol, const __nv_bfloat16 *wb, const float *bias,
-           float *y, const int32_t *out_rows, double *bn_sums, cudaStream_t st) {
+           float *y, const int32_t *out_rows, const uint32_t *tile_masks, double *bn_sums, cudaStream_t st) {
     using C = Cfg<CIN, COUT>;
     CUtensorMap mx, mw;
     if (int rc = make_map(&mx, xb, (uint64_t)n_in, CIN, 1, C::kRowElems)) return rc;              // gather4: box = one row
@@ -364,7 +380,7 @@ int launch(const __nv_bfloat16 *xb, int n_in, const int32_t *nbr, int n_out, int
         TODA_CUDA_OK(cudaFuncSetAttribute(conv_tma_fwd_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
         attr_set = true;
     }
-    conv_tma_fwd_kernel<CIN, COUT><<<grid, kThreads, C::kSmem, st>>>(mx, mw, nbr, n_in, n_out, kvol, bias, y, out_rows, bn_sums, num_tiles);
+    conv_tma_fwd_kernel<CIN, COUT><<<grid, kThreads, C::kSmem, st>>>(mx, mw, nbr, n_in, n_out, kvol, bias, y, out_rows, tile_masks, bn_sums, num_tiles);
     TODA_LAUNCH_OK();
     return TODA_OK;
 }
@@ -377,14 +393,15 @@ int conv_tma_make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t c
 
 // xb: bf16 [n_in][cin], wb: bf16 [cout][kvol*cin]; cin, cout in {16,32,64,128}
 int conv_tma_fwd(const void *xb, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const void *wb, int cout,
-                 const float *bias, float *y, const int32_t *out_rows, double *bn_sums, cudaStream_t st) {
+                 const float *bias, float *y, const int32_t *out_rows, const uint32_t *tile_masks, double *bn_sums,
+                 cudaStream_t st) {
     const __nv_bfloat16 *x = (const __nv_bfloat16 *)xb, *w = (const __nv_bfloat16 *)wb;
 #define CASE_CO(CI)                                                                                    \
     switch (cout) {                                                                                    \
-        case 16: return launch<CI, 16>(x, n_in, nbr, n_out, kvol, w, bias, y, out_rows, bn_sums, st);                     \
-        case 32: return launch<CI, 32>(x, n_in, nbr, n_out, kvol, w, bias, y, out_rows, bn_sums, st);                     \
-        case 64: return launch<CI, 64>(x, n_in, nbr, n_out, kvol, w, bias, y, out_rows, bn_sums, st);                     \
-        case 128: return launch<CI, 128>(x, n_in, nbr, n_out, kvol, w, bias, y, out_rows, bn_sums, st);                   \
+        case 16: return launch<CI, 16>(x, n_in, nbr, n_out, kvol, w, bias, y, out_rows, tile_masks, bn_sums, st);                     \
+        case 32: return launch<CI, 32>(x, n_in, nbr, n_out, kvol, w, bias, y, out_rows, tile_masks, bn_sums, st);                     \
+        case 64: return launch<CI, 64>(x, n_in, nbr, n_out, kvol, w, bias, y, out_rows, tile_masks, bn_sums, st);                     \
+        case 128: return launch<CI, 128>(x, n_in, nbr, n_out, kvol, w, bias, y, out_rows, tile_masks, bn_sums, st);                   \
     }                                                                                                  \
     break;
     switch (cin) {

@@ -256,6 +256,8 @@ class GeometryPlan:
         out = [self.coords, self.index.frame_counts]
         for rb, index_out in self.indice_dict.values():
             out += [rb.out_coords, rb.nbr_fwd]
+            if rb.tile_masks is not None:
+                out.append(rb.tile_masks)
             if rb.nbr_bwd is not None:
                 out.append(rb.nbr_bwd)
             if index_out.frame_counts is not None:
