@@ -559,11 +559,11 @@ int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int
     int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;   // persistent: one CTA per SM walks the tiles
     CUtensorMap map_w;
     if (int rc = conv_tma_make_map(&map_w, wb, (uint64_t)cout, (uint64_t)kvol * cin, (uint32_t)cout, kChunkK)) return rc;
-    // K blocks per chunk: 2 for Cout <= 64 unless TODA_TC_KB=1 (A/B measurements)
-    static int kb_env = -1;
-    if (kb_env < 0) { const char *e = getenv("TODA_TC_KB"); kb_env = e ? atoi(e) : 0; }
-#define LAUNCH_TC_KB(CI, CO, KB_)                                                                                            \
+    // K blocks per chunk: 2 for Cout <= 64 (8 MMAs per barrier round trip), 1 for Cout = 128 (more stages); the A/B is in
+    // profiles/r01_feed_ab.md
+#define LAUNCH_TC(CI, CO)                                                                                                    \
     do {                                                                                                                     \
+        constexpr int KB_ = (CO) <= 64 ? 2 : 1;                                                                              \
         constexpr int smem = FwdCfg<CO, KB_>::kSmem;                                                                         \
         static bool attr_set = false;                                                                                        \
         if (!attr_set) {                                                                                                     \
@@ -571,11 +571,6 @@ int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int
             attr_set = true;                                                                                                 \
         }                                                                                                                    \
         conv_tc_fwd_kernel<CI, CO, KB_><<<grid, kFwdThreads, smem, st>>>(xb, nbr, n_out, kvol, map_w, bias, y, out_rows, tile_masks, bn_sums, num_tiles, g_dbg_timeline); \
-    } while (0)
-#define LAUNCH_TC(CI, CO)                                                                                                    \
-    do {                                                                                                                     \
-        if ((CO) <= 64 && kb_env != 1) LAUNCH_TC_KB(CI, CO, ((CO) <= 64 ? 2 : 1));                                           \
-        else LAUNCH_TC_KB(CI, CO, 1);                                                                                        \
     } while (0)
 #define LAUNCH_TC_CO(CI)                                                                                 \
     switch (cout) {                                                                                      \
@@ -594,7 +589,6 @@ int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int
     }
 #undef LAUNCH_TC_CO
 #undef LAUNCH_TC
-#undef LAUNCH_TC_KB
     TODA_LAUNCH_OK();
     return TODA_OK;
 }
