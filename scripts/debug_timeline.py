@@ -14,14 +14,14 @@ index.insert(torch.from_numpy(idx).cuda()); index.build(n)
 rb = ops.rulebook_subm(index, [3, 3, 3])
 w = torch.randn(cout, 3, 3, 3, cin, device="cuda") * 0.1
 L = _C.lib()
-buf = torch.zeros(7 * 256, dtype=torch.int64, device="cuda")
+buf = torch.zeros(8 * 256, dtype=torch.int64, device="cuda")
 for _ in range(3): ops.sparse_conv(x, w, None, rb, ops.CONV_BF16)
 L.toda_debug_set_timeline.argtypes = [ctypes.c_void_p]
 L.toda_debug_set_timeline(ctypes.c_void_p(buf.data_ptr()))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); ops.sparse_conv(x, w, None, rb, ops.CONV_BF16); e1.record(); torch.cuda.synchronize()
 L.toda_debug_set_timeline(None)
-t = buf.cpu().numpy().reshape(7, 256).astype(np.int64)
+t = buf.cpu().numpy().reshape(8, 256).astype(np.int64)[:7]
 t0 = t[4, 1]
 names = ["M:fenced", "M:mma0", "M:mma_last", "P:signalled", "M:wait full", "M:full ok", "M:committed"]
 print("conv %d->%d n=%d: %.3f ms (incl. pre-passes)" % (cin, cout, n, e0.elapsed_time(e1)))

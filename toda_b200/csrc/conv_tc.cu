@@ -250,7 +250,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
         int g = 0, it = 0;              // global chunk counter (stage ring position), tile counter
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int ib = it & 1;
+            if (dbg && blockIdx.x == 0 && tid == 0 && it < 256) dbg[0 * 256 + it] = clock64();      // tile start (before the slice wait)
             mbar_wait(idx_full + 8 * ib, (it >> 1) & 1);
+            if (dbg && blockIdx.x == 0 && tid == 0 && it < 256) dbg[1 * 256 + it] = clock64();      // slice there
+            if (dbg && blockIdx.x == 0 && tid == 0 && it < 255) dbg[7 * 256 + it] = g;              // first chunk index of the tile
             const uint32_t idx_tile = idx_lane + ib * kIdxBytes;
             for (unsigned long long cm = chunk_mask_of(t); cm; cm &= cm - 1, ++g) {
                 const int c = __ffsll((long long)cm) - 1;
@@ -398,6 +401,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(acc_empty + 8 * ab);
+            if (dbg && blockIdx.x == 0 && q == 1 && lane == 0 && it < 256) dbg[2 * 256 + it] = clock64();   // tile drained
         }
         if (bn_sums && !(lane & 1)) {
             // lane l (even) owns column n0 + ((l >> 1) & 15); one fp64 atomic per CTA-warp and channel
@@ -501,7 +505,7 @@ int conv_tma_fwd(const void *xb, int n_in, int cin, const int32_t *nbr, int n_ou
 // 2-D bf16 row-major tensor map [rows][cols] with box [box_rows][box_cols], swizzle by box row bytes (conv_tma.cu)
 int conv_tma_make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols);
 
-// development aid: device buffer (7 x 256 clock64 samples) filled by CTA 0 of the cp.async forward kernel
+// development aid: device buffer (8 x 256 int64: clock64 samples per chunk / per tile) filled by CTA 0 of the cp.async forward kernel
 static long long *g_dbg_timeline = nullptr;
 extern "C" void toda_debug_set_timeline(long long *buf) { g_dbg_timeline = buf; }
 
