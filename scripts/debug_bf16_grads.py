@@ -1,7 +1,7 @@
 """Per-layer relative L2 difference between the bf16 tensor-core path and the fp32 FFMA path (one full frame)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 import toda_b200.pcdet_plugin as P
 from toda_b200 import ops, synth
 from toda_b200.spconv_compat import pytorch as G

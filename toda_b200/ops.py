@@ -4,7 +4,7 @@ graph); every device-side computation is a kernel of libtoda_b200.so.  No CPU fa
 """
 import ctypes
 import weakref
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import List, Optional
 
 import numpy as np
