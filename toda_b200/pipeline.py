@@ -69,12 +69,17 @@ class InputPipeline:
                     bd[key] = t
             before = set(id(v) for v in bd.values() if torch.is_tensor(v))
             bd = self.vfe(bd)
-            canonical = bool(bd.get("voxel_coords_canonical", False))
-            plan = self.backbone.plan_geometry(bd["voxel_coords"], int(bd["batch_size"]), canonical=canonical)
-            bd["spconv_geometry"] = plan
+            plan = None
+            if bd.get("voxel_coords_canonical", False):
+                # (voxels that arrive in another row order, e.g. voxelized on the host, are put in canonical order by the
+                # backbone's first layer together with their features: nothing to plan ahead without the features)
+                plan = self.backbone.plan_geometry(bd["voxel_coords"], int(bd["batch_size"]), canonical=True)
+                bd["spconv_geometry"] = plan
             ready = torch.cuda.Event()
             ready.record(self.stream)
-        tensors = staged + [v for v in bd.values() if torch.is_tensor(v) and id(v) not in before] + plan.tensors()
+        tensors = staged + [v for v in bd.values() if torch.is_tensor(v) and id(v) not in before]
+        if plan is not None:
+            tensors += plan.tensors()
         return _Handle(bd, ready, tensors)
 
     def consume(self, handle):
