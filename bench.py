@@ -307,7 +307,7 @@ def run_ours(args, rank, world, local_rank):
         nxt = front(hp, ho, False)                   # H2D of the next batch from pinned memory, on the side stream
         return float(loss.item()), nxt               # D2H read of this step's result
     h = front(*hosts[0], False)
-    for i in range(max(1, args.warmup // 2)):
+    for i in range(max(2, args.warmup)):          # (the H2D path and its side-pool size classes warm up too)
         _, h = e2e_step(h, i)
     barrier()
     e0.record()
