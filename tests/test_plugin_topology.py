@@ -61,3 +61,22 @@ def test_golden_voxelizer_fixture_matches_oracle():
         assert list(g.grid) == list(c["grid_size"])
         np.testing.assert_allclose(OV.mean_vfe(v, n), c["voxel_features"], rtol=1e-6, atol=1e-7)
     assert cases["crop_nus_capped"]["voxels"].shape[0] == 700      # the max_voxels cap is active in this case
+
+
+def test_point_preprocessor_two_phase_protocol_on_cpu():
+    """Construction binds the configured steps in order and publishes grid_size / voxel_size like the reference's
+    DataProcessor (data_processor.py L64-76, L105-113); no CUDA call is made until a batch is processed."""
+    import pytest
+    from toda_b200.pcdet_plugin.processor import PointPreprocessor
+    from tests.parity_utils import Cfg
+    cfgs = [Cfg(NAME="mask_points_and_boxes_outside_range", REMOVE_OUTSIDE_BOXES=True),
+            Cfg(NAME="shuffle_points", SHUFFLE_ENABLED=Cfg(train=True, test=False)),
+            Cfg(NAME="transform_points_to_voxels_placeholder", VOXEL_SIZE=[0.075, 0.075, 0.2])]
+    pp = PointPreprocessor(cfgs, np.array([-54.0, -54.0, -5.0, 54.0, 54.0, 3.0], np.float32), training=False, num_point_features=5)
+    assert pp.grid_size.tolist() == [1440, 1440, 40] and pp.voxel_size == [0.075, 0.075, 0.2] and pp.mode == "test"
+    assert len(pp.data_processor_queue) == 3
+    # shuffle disabled in test mode: the bound step returns the dict untouched (no device work)
+    marker = object()
+    assert pp.data_processor_queue[1](data_dict={"points": marker})["points"] is marker
+    with pytest.raises(NotImplementedError):
+        PointPreprocessor([Cfg(NAME="transform_points_to_voxels", VOXEL_SIZE=[0.1, 0.1, 0.2])], np.zeros(6, np.float32), True, 5)

@@ -33,12 +33,13 @@ class PointPreprocessor:
         self.mode = "train" if training else "test"
         self.grid_size = self.voxel_size = None
         self.data_processor_queue = []
-        for cur_cfg in processor_configs:
-            name = cur_cfg["NAME"] if isinstance(cur_cfg, dict) else cur_cfg.NAME
-            if not hasattr(self, name):
+        for step_cfg in processor_configs:
+            name = step_cfg["NAME"] if isinstance(step_cfg, dict) else step_cfg.NAME
+            step = getattr(self, name, None)
+            if step is None:
                 raise NotImplementedError(f"PointPreprocessor has no step {name!r} (voxelization happens in the VFE: use "
                                           "transform_points_to_voxels_placeholder)")
-            self.data_processor_queue.append(getattr(self, name)(config=cur_cfg))
+            self.data_processor_queue.append(step(config=step_cfg))      # phase 1: bind the config, get the per-batch callable
 
     @staticmethod
     def _get(cfg, key, default=None):
@@ -80,17 +81,17 @@ class PointPreprocessor:
         return torch.argsort(key).int()
 
     def transform_points_to_voxels_placeholder(self, data_dict=None, config=None):
-        if data_dict is None:
-            vs = self._get(config, "VOXEL_SIZE")
-            grid_size = (self.point_cloud_range[3:6] - self.point_cloud_range[0:3]) / np.array(vs)
-            self.grid_size = np.round(grid_size).astype(np.int64)
-            self.voxel_size = vs
-            return partial(self.transform_points_to_voxels_placeholder, config=config)
-        return data_dict
+        """Voxelization itself happens in the VFE (K1); this step only publishes grid_size / voxel_size, as the
+        reference's placeholder does (data_processor.py L105-113)."""
+        if data_dict is not None:
+            return data_dict
+        self.voxel_size = self._get(config, "VOXEL_SIZE")
+        self.grid_size = ops.grid_size_xyz(self.point_cloud_range, self.voxel_size)
+        return partial(self.transform_points_to_voxels_placeholder, config=config)
 
     def forward(self, data_dict):
-        for cur_processor in self.data_processor_queue:
-            data_dict = cur_processor(data_dict=data_dict)
+        for step in self.data_processor_queue:                            # phase 2: run the bound steps in cfg order
+            data_dict = step(data_dict=data_dict)
         return data_dict
 
 
