@@ -117,10 +117,14 @@ def _load_mixers(ns, P):
     stub = types.ModuleType("pcdet.ops.iou3d_nms.iou3d_nms_utils")
     sys.modules["pcdet.ops.iou3d_nms.iou3d_nms_utils"] = stub
     sys.modules["pcdet.ops.iou3d_nms"].iou3d_nms_utils = stub
-    aug = types.ModuleType("pcdet.datasets.augmentor.augmentor_utils")
-    aug.get_points_in_box = None      # only used by the collision-detection variant, not exercised
-    sys.modules["pcdet.datasets.augmentor.augmentor_utils"] = aug
-    sys.modules["pcdet.datasets.augmentor"].augmentor_utils = aug
+    try:      # pure numpy (get_points_in_box L474-491); imports only common_utils / box_utils, both loaded above
+        ns.augmentor_utils = _load("pcdet.datasets.augmentor.augmentor_utils", f"{P}/datasets/augmentor/augmentor_utils.py")
+    except Exception:
+        aug = types.ModuleType("pcdet.datasets.augmentor.augmentor_utils")
+        aug.get_points_in_box = None      # only used by the collision-detection variant, not exercised
+        sys.modules["pcdet.datasets.augmentor.augmentor_utils"] = aug
+        sys.modules["pcdet.datasets.augmentor"].augmentor_utils = aug
+        ns.augmentor_utils = None
     ns.cutmix = _load("pcdet.datasets.processor.inter_domain_point_cutmix", f"{P}/datasets/processor/inter_domain_point_cutmix.py")
     ns.polarmix = _load("pcdet.datasets.processor.inter_domain_point_polarmix",
                         f"{P}/datasets/processor/inter_domain_point_polarmix.py")

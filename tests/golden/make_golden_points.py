@@ -136,6 +136,16 @@ def main():
     out["mixup/result"] = mixed["points"].astype(np.float32)
     print("mixup:", m1.shape, m2.shape, "lam", out["mixup/lam"], "->", mixed["points"].shape)
 
+    # ---- f-1 (box side, first piece): get_points_in_box, pure numpy in the reference (augmentor_utils.py L474-491)
+    bp = small_frame("nus_0075", 9, 6000, window=25.0)[:, :5]
+    rngb = np.random.default_rng(SEED + 3)
+    centres = bp[rngb.integers(0, bp.shape[0], 6), :3]
+    boxes_pb = np.concatenate([centres, rngb.uniform([1.5, 1.0, 1.0], [8.0, 4.0, 3.0], (6, 3)), rngb.uniform(-np.pi, np.pi, (6, 1)),
+                               np.ones((6, 1))], axis=1).astype(np.float32)
+    masks = np.stack([ns.augmentor_utils.get_points_in_box(bp, b)[1] for b in boxes_pb])
+    out["inbox/points"], out["inbox/boxes"], out["inbox/masks"] = bp, boxes_pb, masks
+    print("points in boxes:", bp.shape, "boxes", boxes_pb.shape, "inside counts", masks.sum(1))
+
     # ---- a-2: collate (three numpy lines of dataset.py L173-178, restated; see the module docstring)
     frames = [small_frame("nus_0075", 7 + i, 700 + 100 * i) for i in range(3)]
     collated = np.concatenate([np.pad(f, ((0, 0), (1, 0)), mode="constant", constant_values=i) for i, f in enumerate(frames)], axis=0)
