@@ -185,6 +185,23 @@ int toda_spconv_fwd(const float *x, const void *x_bf16, int n_in, int cin, const
                     const float *w, int cout, const float *bias, float *y, const int32_t *out_rows,
                     const uint32_t *tile_masks, double *bn_sums, int precision, void *workspace, size_t workspace_bytes,
                     void *stream);
+/* Tile plan (row cache of the TODA_CONV_BF16 kernel): for every 128-row tile of a neighbour table and every group of
+ * kvol/ngroups consecutive offsets (ngroups = kz: the neighbours of one group lie in one z plane), the ascending list of
+ * DISTINCT input rows the tile gathers (`rows`: int32, `cap` entries reserved per (tile, group); `cnt`: int32 per
+ * (tile, group), entries used) and the table rewritten as 16-bit slots into that list (`lidx`: uint16
+ * [tiles][kvol][128]; 0xFFFF = no neighbour, 0xFFFE = not in the list, read the row through `nbr`).  With a plan the
+ * convolution loads each distinct row once per tile into shared memory and feeds tcgen05.mma's A operand from tensor
+ * memory.  cap = toda_tile_plan_capacity(channels of the gathered rows) (<= 512).  toda_spconv_fwd_plan is
+ * toda_spconv_fwd with the plan and an optional `addend` ([n_out][cout] fp32, added to y in the epilogue: the
+ * residual-branch gradient in SparseBasicBlock's backward, spconv_backbone.py L63). */
+int toda_tile_plan_capacity(int channels);
+int toda_table_tile_plan(const int32_t *nbr, int n_out, int kvol, int ngroups, int cap, uint16_t *lidx, int32_t *rows,
+                         int32_t *cnt, void *stream);
+int toda_spconv_fwd_plan(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
+                         const float *w, int cout, const float *bias, const float *addend, float *y,
+                         const int32_t *out_rows, const uint32_t *tile_masks, const uint16_t *plan_lidx,
+                         const int32_t *plan_rows, const int32_t *plan_cnt, int plan_groups, int plan_cap, double *bn_sums,
+                         int precision, void *workspace, size_t workspace_bytes, void *stream);
 size_t toda_spconv_wgrad_workspace_bytes(int n_in, int n_out, int kvol, int cin, int cout, int precision);
 int toda_spconv_wgrad(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
                       const float *dy, const void *dy_bf16, int cout, float *dw_param, void *workspace,

@@ -42,6 +42,10 @@ SIGNATURES = {
     "toda_table_tile_masks": (c_int, [c_vp, c_int, c_int, c_vp, c_vp]),
     "toda_spconv_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp,
                                 c_sz, c_vp]),
+    "toda_tile_plan_capacity": (c_int, [c_int]),
+    "toda_table_tile_plan": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "toda_spconv_fwd_plan": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                     c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp, c_sz, c_vp]),
     "toda_spconv_wgrad_workspace_bytes": (c_sz, [c_int] * 6),
     "toda_spconv_wgrad": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_sz, c_int, c_vp]),
     "toda_bn_workspace_bytes": (c_sz, [c_int]),

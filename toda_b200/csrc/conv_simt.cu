@@ -4,11 +4,12 @@
 // No scatter, no atomics: every output row is written exactly once (deterministic).
 // The tcgen05 path (conv_tc.cu) has the same structure with the accumulator in TMEM.
 #include "common.cuh"
+#include "conv_ts.cuh"
 
 int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *w,
                 int cout, const float *bias, float *y, const int32_t *out_rows, const uint32_t *tile_masks, double *bn_sums,
                 void *workspace, size_t workspace_bytes,
-                cudaStream_t st);
+                cudaStream_t st, const TilePlan *plan, const float *addend);
 size_t conv_tc_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol);
 int conv_tc_wgrad(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
                   const float *dy, const void *dy_bf16, int cout, float *dw_param, void *workspace, size_t workspace_bytes,
@@ -263,10 +264,33 @@ extern "C" size_t toda_spconv_fwd_workspace_bytes(int n_in, int cin, int cout, i
     return 0;
 }
 
+static int spconv_fwd_impl(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
+                           const float *w, int cout, const float *bias, float *y, const int32_t *out_rows,
+                           const uint32_t *tile_masks, double *bn_sums, int precision, void *workspace, size_t workspace_bytes,
+                           void *stream, const TilePlan *plan, const float *addend);
+
 extern "C" int toda_spconv_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
                                const float *w, int cout, const float *bias, float *y, const int32_t *out_rows,
                                const uint32_t *tile_masks, double *bn_sums, int precision,
                                void *workspace, size_t workspace_bytes, void *stream) {
+    return spconv_fwd_impl(x, x_bf16, n_in, cin, nbr, n_out, kvol, w, cout, bias, y, out_rows, tile_masks, bn_sums, precision, workspace,
+                           workspace_bytes, stream, nullptr, nullptr);
+}
+
+extern "C" int toda_spconv_fwd_plan(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
+                                    const float *w, int cout, const float *bias, const float *addend, float *y,
+                                    const int32_t *out_rows, const uint32_t *tile_masks, const uint16_t *plan_lidx,
+                                    const int32_t *plan_rows, const int32_t *plan_cnt, int plan_groups, int plan_cap, double *bn_sums,
+                                    int precision, void *workspace, size_t workspace_bytes, void *stream) {
+    TilePlan plan{plan_lidx, plan_rows, plan_cnt, plan_groups, plan_cap};
+    return spconv_fwd_impl(x, x_bf16, n_in, cin, nbr, n_out, kvol, w, cout, bias, y, out_rows, tile_masks, bn_sums, precision, workspace,
+                           workspace_bytes, stream, plan_lidx ? &plan : nullptr, addend);
+}
+
+static int spconv_fwd_impl(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
+                           const float *w, int cout, const float *bias, float *y, const int32_t *out_rows,
+                           const uint32_t *tile_masks, double *bn_sums, int precision, void *workspace, size_t workspace_bytes,
+                           void *stream, const TilePlan *plan, const float *addend) {
     TODA_CHECK_ARG(n_in >= 0 && n_out >= 0 && cin > 0 && cout > 0 && kvol > 0, "spconv_fwd: bad sizes");
     if (n_out == 0) return TODA_OK;
     TODA_CHECK_ARG(x && nbr && w && y, "spconv_fwd: null pointer");
@@ -276,7 +300,8 @@ extern "C" int toda_spconv_fwd(const float *x, const void *x_bf16, int n_in, int
     // Cout in {16,32,64,128}; anything else (e.g. the dgrad of the 4/5-channel input layer) runs on the FFMA kernel.
     if (precision == TODA_CONV_BF16 && conv_tc_supported(cin, cout, kvol))
         return conv_tc_fwd(x, x_bf16, n_in, cin, nbr, n_out, kvol, w, cout, bias, y, out_rows, tile_masks, bn_sums, workspace,
-                           workspace_bytes, st);
+                           workspace_bytes, st, plan, addend);
+    TODA_CHECK_ARG(!addend, "spconv_fwd: a fused addend needs the tensor-core tile-plan kernel for this shape");
     TODA_CHECK_ARG(!bn_sums, "spconv_fwd: fused BatchNorm statistics need the tensor-core kernel for this shape");
     if (cout <= 16) {
         dim3 grid(ceil_div(n_out, 256), ceil_div(cout, 16));

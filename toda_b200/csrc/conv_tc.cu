@@ -21,6 +21,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "conv_ts.cuh"
 #include "epilogue.cuh"
 #include "table_slice.cuh"
 
@@ -502,12 +503,14 @@ static inline int pad16(int c) { return c < 16 ? 16 : c; }
 int conv_tma_fwd(const void *xb, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const void *wb, int cout,
                  const float *bias, float *y, const int32_t *out_rows, const uint32_t *tile_masks, double *bn_sums,
                  cudaStream_t st);
-// 2-D bf16 row-major tensor map [rows][cols] with box [box_rows][box_cols], swizzle by box row bytes (conv_tma.cu)
-int conv_tma_make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols);
 
 // development aid: device buffer (8 x 256 int64: clock64 samples per chunk / per tile) filled by CTA 0 of the cp.async forward kernel
 static long long *g_dbg_timeline = nullptr;
 extern "C" void toda_debug_set_timeline(long long *buf) { g_dbg_timeline = buf; }
+long long *conv_tc_debug_timeline() { return g_dbg_timeline; }
+static int g_dbg_mode = 0;
+extern "C" void toda_debug_set_mode(int m) { g_dbg_mode = m; }
+int conv_tc_debug_mode() { return g_dbg_mode; }
 
 bool conv_tc_supported(int cin, int cout, int kvol) {
     bool cin_ok = (cin >= 1 && cin < 16) || cin == 16 || cin == 32 || cin == 64 || cin == 128;
@@ -522,7 +525,7 @@ size_t conv_tc_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol) {
 int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *w,
                 int cout, const float *bias, float *y, const int32_t *out_rows, const uint32_t *tile_masks, double *bn_sums,
                 void *workspace, size_t workspace_bytes,
-                cudaStream_t st) {
+                cudaStream_t st, const TilePlan *plan, const float *addend) {
     size_t need = conv_tc_fwd_workspace_bytes(n_in, cin, cout, kvol);
     if (!workspace || workspace_bytes < need) {
         toda_set_error("spconv_fwd(bf16): workspace %zu < required %zu bytes", workspace_bytes, need);
@@ -552,7 +555,15 @@ int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int
     // whatever the row width, so the cp.async producers below are faster for narrower rows.
     // TODA_TC_FEED=tma|cpasync forces one of them (A/B measurements).
     static int feed = -1;
-    if (feed < 0) { const char *e = getenv("TODA_TC_FEED"); feed = !e ? 2 : (e[0] == 'c' ? 0 : 1); }
+    if (feed < 0) { const char *e = getenv("TODA_TC_FEED"); feed = !e ? 2 : (e[0] == 'c' ? 0 : (e[0] == 't' && e[1] == 'm' ? 1 : 2)); }
+    // with a tile plan (toda_table_tile_plan) the row-cache / TMEM-operand kernel takes every supported shape
+    // (TODA_TC_FEED=tma|cpasync keeps the round-1 kernels for A/B measurements)
+    if (feed == 2 && conv_ts_supported(cin, cout, kvol, plan))
+        return conv_ts_fwd(xb, n_in, cin, nbr, n_out, kvol, *plan, wb, cout, bias, addend, y, out_rows, tile_masks, bn_sums, st);
+    if (addend) {
+        toda_set_error("spconv_fwd: a fused addend needs the tile-plan kernel (plan missing or shape unsupported)");
+        return TODA_ERR_UNSUPPORTED;
+    }
     if (feed == 1 || (feed == 2 && cin == 128 && cout == 128))
         {
         // (raster-order masks skip ~17 % of the 128-channel chunks but measured slower on this kernel -- the skipped chunks

@@ -1,0 +1,813 @@
+// K5/K6 sparse convolution, row-cache + TMEM-operand variant of the tcgen05 implicit GEMM ("TS" kernel).
+//
+//   y[o, :] = bias + sum_{k, ci} x[nbr[k,o], ci] * w[k, ci, :]  (+ addend[o, :])      bf16 operands, fp32 accumulate
+//
+// Why another kernel: conv_tc.cu / conv_tma.cu gather every A row from L2 once per (offset, output row) -- in raster
+// order the same input row is fetched 2.5-4 times per 128-row tile (profiles/r01_feed_ab.md) -- and every A byte crosses
+// the shared-memory port twice more (written by the copy, read by the MMA).  Here
+//   * a plan-time pass (tile_plan_kernel) lists, per tile and per kz-group of offsets, the DISTINCT input rows the tile
+//     touches and rewrites the neighbour table into 16-bit slot numbers into that list;
+//   * a loader warp copies those rows ONCE (cp.async, 16-byte pieces, contiguous row runs coalesce) into a padded
+//     shared-memory slab, one offset group ahead of its use;
+//   * eight gather warps (thread = output row = TMEM lane) read their row's neighbour out of the slab (16-byte
+//     ld.shared, conflict-free thanks to the 16-byte row padding) and write it with tcgen05.st straight into TENSOR
+//     MEMORY, where tcgen05.mma takes its A operand from (the ".ts" form: A in TMEM, lane = row, two bf16 per 32-bit
+//     column).  The A tile never exists in shared memory; rows without a neighbour are zero registers.
+//   * B (weights, K-major SWIZZLE_128B) still arrives by tiled TMA; accumulators are double-buffered in TMEM and
+//     drained by four epilogue warps (bias, optional addend, BatchNorm statistics) while the next tile is multiplied.
+// TMEM map (512 columns): [0, 2*COUT) two accumulators, [256, 512) a ring of eight 32-column A blocks (64 K elements).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "conv_ts.cuh"
+#include "epilogue.cuh"
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kMaxKvol = 27;
+constexpr int kLidxBytes = 7168;                  // >= 27 * 128 * 2, 1024-multiple
+constexpr uint32_t kLidxNone = 0xFFFFu;           // no neighbour under this offset
+constexpr uint32_t kLidxGlobal = 0xFFFEu;         // neighbour exists but is not in the slab: read it from global memory
+constexpr int kGatherWarps = 8;
+// the warp scheduler favours high warp ids: the latency-critical gather warps get them
+constexpr int kWarpMma = 4, kWarpLoader = 5, kWarpB = 6, kWarpLoader2 = 7, kWarpGather0 = 8;
+constexpr int kThreads = 16 * 32;
+constexpr int kASlots = 8;
+constexpr int kACol0 = 256;
+constexpr int kPlanWindow = 32768;                // row-id window of the plan kernel's bitmap
+constexpr int kMaxBatches = 16;                   // slab capacity <= 512 rows
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (!done) {
+        // (the last operand is the suspend-time hint in ns: the thread sleeps in hardware until the phase completes or the
+        // time is up, so a waiting role re-issues a handful of instructions per 16 us instead of spinning next to the
+        // gather warps it shares a scheduler with; an arrival wakes it at once)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity), "r"(0x4000u)
+            : "memory");
+        if (!done && ++spins > (1u << 20)) __trap();   // a lost arrival must not hang the GPU box
+    }
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]: A = 128 lanes x 8 columns (16 bf16 per lane), B = K-major SWIZZLE_128B descriptor
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, see conv_tc.cu)
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d) {
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return (uint32_t)v;
+}
+
+template <int CIN, int COUT> struct TsCfg {
+    static constexpr int kRowBytes = CIN * 2;
+    static constexpr int kStride = kRowBytes + 16;             // (stride / 16) odd: 8 consecutive slots hit 8 different 16-byte bank groups
+    static constexpr int kNB = CIN == 128 ? 2 : 3;             // slab buffers (one per offset group in flight)
+    static constexpr int kSlab = CIN == 128 ? 65536 : (CIN == 64 ? 40960 : (CIN == 32 ? 32768 : 24576));
+    static constexpr int kCap = kSlab / kStride - 1;           // 239 / 283 / 408 / 511 rows + the all-zero row at slot `cap`
+    static constexpr int kBStage = COUT * 128;                 // [COUT rows][64 bf16]
+    static constexpr int kNkbMax = (kMaxKvol * CIN + 63) / 64;
+    // small layers keep ALL their weights in shared memory for the lifetime of the (persistent) CTA: no per-tile re-fetch
+    // (at 32->32 the weights were more than half of the L2->SM bytes of a tile)
+    static constexpr bool kBRes = kNkbMax * kBStage <= 57344;
+    static constexpr int kSB = kBRes ? kNkbMax : (COUT == 128 ? 4 : (COUT == 64 ? 6 : 8));
+    static constexpr int kParts = CIN >= 64 ? 1 : 64 / CIN;    // kernel offsets per 64-element K block
+    static constexpr int kPV = (CIN >= 64 ? 64 : CIN) / 8;     // 16-byte vectors per part
+    static constexpr int kSmemRaw = 1024 + kSB * kBStage + kNB * kSlab + 2 * kLidxBytes + 512;
+    // the kernel allocates all 512 TMEM columns: never let two CTAs share an SM (the second would wait in tcgen05.alloc)
+    static constexpr int kSmem = kSmemRaw < 120 * 1024 ? 120 * 1024 : kSmemRaw;
+    static_assert(kCap <= 32 * kMaxBatches, "slab capacity");
+    static_assert(2 * COUT <= kACol0, "accumulators overlap the A ring");
+    static constexpr int kBBars = kBRes ? 1 : kSB;             // resident weights arrive on one barrier, once
+    static_assert(kBBars <= 14, "barrier area");
+};
+
+#define TS_STTM_X32(addr, v)                                                                                                        \
+    asm volatile(                                                                                                                   \
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"     \
+        "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"                                                                         \
+        ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),  \
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),   \
+          "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),   \
+          "r"(v[30]), "r"(v[31])                                                                                                    \
+        : "memory")
+
+// Roles (16 warps): 0-3 epilogue, 4 MMA issuer, 5 + 7 slab loaders, 6 weight producer, 8-15 gather (two warpgroups,
+// thread = tile row = TMEM lane).
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfloat16 *__restrict__ xb, const int *__restrict__ nbr,
+                                                                  int n_out, int kvol, const uint16_t *__restrict__ lidx,
+                                                                  const int *__restrict__ prow, const int *__restrict__ pcnt,
+                                                                  int ngroups, int cap,
+                                                                  const __grid_constant__ CUtensorMap map_w /*[COUT][kvol*CIN] bf16*/,
+                                                                  const float *__restrict__ bias, const float *__restrict__ addend,
+                                                                  float *__restrict__ y, const int *__restrict__ out_rows,
+                                                                  const uint32_t *__restrict__ tile_masks,
+                                                                  double *__restrict__ bn_sums, int num_tiles, long long *__restrict__ dbg, int xmode) {
+    using C = TsCfg<CIN, COUT>;
+    constexpr int NB = C::kNB, SB = C::kSB, PARTS = C::kParts, PV = C::kPV;
+    constexpr bool BRES = C::kBRes;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;          // B stages: SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t slab_base = base + SB * C::kBStage;
+    const uint32_t lidx_base = slab_base + NB * C::kSlab;
+    const uint32_t bar_base = lidx_base + 2 * kLidxBytes;
+    const uint32_t a_full = bar_base, a_empty = bar_base + 64;               // 8 + 8
+    const uint32_t b_full = bar_base + 128, b_empty = bar_base + 240;         // 14 + 14
+    const uint32_t acc_full = bar_base + 352, acc_empty = bar_base + 368;     // 2 + 2
+    const uint32_t slab_full = bar_base + 384, slab_empty = bar_base + 408;   // 3 + 3
+    const uint32_t lidx_full = bar_base + 432, lidx_empty = bar_base + 448;   // 2 + 2
+    const uint32_t tmem_slot = bar_base + 464;
+    volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *)(smem_raw + (tmem_slot - raw));
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nkb = (kvol * CIN + 63) / 64;                // 64-element K blocks
+    const int gs = kvol / ngroups, gs2 = 2 * gs;           // offsets per group; group of offset k = (k >= gs) + (k >= 2 gs)
+    // K blocks of tile t that hold at least one real neighbour (bit c = K block c); every role derives the same list.
+    // A tile without any neighbour still walks block 0 (all-zero rows) so that its accumulator is defined.
+    // (the offset mask of the NEXT tile is fetched while the current tile is processed: load_om / kb_mask_from)
+    auto load_om = [&](int t) -> uint32_t { return (tile_masks && t < num_tiles) ? __ldg(tile_masks + t) : 0xffffffffu; };
+    auto kb_mask_from = [&](uint32_t om) -> unsigned long long {
+        if (!tile_masks) return nkb >= 64 ? ~0ull : ((1ull << nkb) - 1ull);
+        unsigned long long cm = 0ull;
+        if (CIN <= 64) {
+            for (int c = 0; c < nkb; ++c)
+                if ((om >> (c * PARTS)) & ((1u << PARTS) - 1u)) cm |= 1ull << c;
+        } else {
+            for (int c = 0; c < nkb; ++c)
+                if ((om >> (c >> 1)) & 1u) cm |= 1ull << c;
+        }
+        return cm ? cm : 1ull;
+    };
+    auto kb_mask_of = [&](int t) -> unsigned long long { return kb_mask_from(load_om(t)); };
+
+    if (tid == 0) {
+        for (int s = 0; s < kASlots; ++s) {
+            mbar_init(a_full + 8 * s, 4);          // the four warps of the gathering warpgroup
+            mbar_init(a_empty + 8 * s, 1);         // tcgen05.commit
+        }
+        for (int s = 0; s < C::kBBars; ++s) {
+            mbar_init(b_full + 8 * s, 1);          // arrive.expect_tx; the TMA completes the bytes
+            mbar_init(b_empty + 8 * s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(acc_full + 8 * b, 1);
+            mbar_init(acc_empty + 8 * b, 4);       // the four epilogue warps
+            mbar_init(lidx_full + 8 * b, 1);
+            mbar_init(lidx_empty + 8 * b, kGatherWarps);
+        }
+        for (int b = 0; b < NB; ++b) {
+            mbar_init(slab_full + 8 * b, 64);      // one cp.async-completion arrival per lane of the two loader warps
+            mbar_init(slab_empty + 8 * b, kGatherWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kWarpMma) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp == kWarpB && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    if (tid < NB * (C::kRowBytes / 16)) {
+        // the all-zero row of every slab (slot `cap`; the loaders only ever write slots < cap)
+        const int b = tid / (C::kRowBytes / 16), pc = tid % (C::kRowBytes / 16);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(slab_base + b * C::kSlab + cap * C::kStride + pc * 16), "r"(0u) : "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    // development aid (scripts/debug_timeline_ts.py): clock64 samples of CTA 0, 16 rows x 256 entries
+#define TS_DBG(cond, rowi, idx) do { if (dbg && blockIdx.x == 0 && (cond) && (idx) < 256) dbg[(rowi) * 256 + (idx)] = clock64(); } while (0)
+
+    if (warp >= kWarpGather0) {
+        // ------------------------------------------------------------------ gather warps: thread = tile row = TMEM lane
+        // The active K blocks of a tile are dealt out in pairs: warpgroup 0 takes pairs 0, 2, ..., warpgroup 1 pairs 1, 3, ...
+        // A pair costs one round of barrier waits / tcgen05.wait::st / arrivals and keeps 2 x 128 bytes per thread in flight.
+        const int wg = (warp - kWarpGather0) >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kACol0;
+        int gbase = 0, it = 0;                          // gbase: global index of this tile's first active K block
+        uint32_t om_next = load_om(blockIdx.x);
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const int ib = it & 1;
+            const uint32_t om = om_next;
+            om_next = load_om(t + gridDim.x);
+            if (!(xmode & 64)) mbar_wait(lidx_full + 8 * ib, (it >> 1) & 1);
+            const uint32_t lidx_tile = lidx_base + ib * kLidxBytes + 2 * row;
+            const int unit0 = it * ngroups;             // (tile, group) units are numbered consecutively per CTA
+            int gwait = 0, gdone = 0;                   // groups of this tile whose slab this warp has waited for / released
+            auto wait_group = [&](int grp) {
+                if (xmode & 32) return;
+                while (gwait <= grp) {
+                    const int u = unit0 + gwait;
+                    mbar_wait(slab_full + 8 * (u % NB), (u / NB) & 1);
+                    ++gwait;
+                }
+            };
+            auto release_below = [&](int grp_end) {
+                // (a warp waits for a slab before releasing it even if it never read it: its arrival must not land in
+                // the barrier phase of the slab's previous use)
+                while (gdone < grp_end && !(xmode & 32)) {
+                    wait_group(gdone);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(slab_empty + 8 * ((unit0 + gdone) % NB));
+                    ++gdone;
+                }
+            };
+            // Branch-free fast path: a row without a neighbour reads the all-zero row kept at slot `cap` of every slab
+            // (all such lanes hit one address: a broadcast); the table entries of the block are fetched first, then
+            // every 16-byte piece.  Returns true if some entry must be read from global memory instead (fix_block).
+            auto load_block = [&](int kb, uint32_t (&v)[32]) -> bool {
+                uint32_t li[PARTS];
+#pragma unroll
+                for (int part = 0; part < PARTS; ++part) {
+                    const int k = CIN == 128 ? (kb >> 1) : kb * PARTS + part;
+                    li[part] = k < kvol ? lds_u16(lidx_tile + (uint32_t)k * (kTileM * 2)) : kLidxNone;
+                }
+                bool fix = false;
+#pragma unroll
+                for (int part = 0; part < PARTS; ++part) {
+                    const int k = CIN == 128 ? (kb >> 1) : kb * PARTS + part;
+                    const uint32_t half = CIN == 128 ? (uint32_t)(kb & 1) * 128u : 0u;
+                    const int grp = (int)(k >= gs) + (int)(k >= gs2);
+                    const uint32_t sl = min(li[part], (uint32_t)cap);
+                    const uint32_t src = slab_base + (uint32_t)((unit0 + grp) % NB) * C::kSlab + sl * C::kStride + half;
+#pragma unroll
+                    for (int q = 0; q < PV; ++q)
+                        lds128(src + 16 * q, v[(part * PV + q) * 4], v[(part * PV + q) * 4 + 1], v[(part * PV + q) * 4 + 2],
+                               v[(part * PV + q) * 4 + 3]);
+                    fix |= li[part] == kLidxGlobal;
+                }
+                return fix;
+            };
+            auto fix_block = [&](int kb, uint32_t (&v)[32]) {
+#pragma unroll
+                for (int part = 0; part < PARTS; ++part) {
+                    const int k = CIN == 128 ? (kb >> 1) : kb * PARTS + part;
+                    const uint32_t half = CIN == 128 ? (uint32_t)(kb & 1) * 128u : 0u;
+                    if (k < kvol && lds_u16(lidx_tile + (uint32_t)k * (kTileM * 2)) == kLidxGlobal) {
+                        const int gi = __ldg(nbr + (size_t)k * n_out + (size_t)t * kTileM + row);
+                        const uint4 *src = (const uint4 *)((const char *)xb + (size_t)gi * C::kRowBytes + half);
+#pragma unroll
+                        for (int q = 0; q < PV; ++q) {
+                            const uint4 r = __ldg(src + q);
+                            v[(part * PV + q) * 4] = r.x; v[(part * PV + q) * 4 + 1] = r.y;
+                            v[(part * PV + q) * 4 + 2] = r.z; v[(part * PV + q) * 4 + 3] = r.w;
+                        }
+                    }
+                }
+            };
+            unsigned long long cm = kb_mask_from(om);
+            const int nact = __popcll(cm);
+            if (dbg && blockIdx.x == 0 && tid == 256 && it < 256) dbg[10 * 256 + it] = gbase;
+            int j = 0;
+            while (cm) {
+                const int kbA = __ffsll((long long)cm) - 1;
+                cm &= cm - 1;
+                int kbB = -1;
+                if (cm) {
+                    kbB = __ffsll((long long)cm) - 1;
+                    cm &= cm - 1;
+                }
+                const int gA = gbase + j;
+                const int pj = j >> 1;
+                j += 2;
+                if ((pj & 1) != wg) continue;
+                TS_DBG((tid & 127) == 0, 0, gA);
+                const int k_first = CIN == 128 ? (kbA >> 1) : kbA * PARTS;
+                release_below((int)(k_first >= gs) + (int)(k_first >= gs2));    // slabs of earlier groups are no longer read by this warp
+                TS_DBG((tid & 127) == 0, 1, gA);
+                {
+                    const int kb_last = kbB >= 0 ? kbB : kbA;
+                    const int k_last = min(CIN == 128 ? (kb_last >> 1) : kb_last * PARTS + PARTS - 1, kvol - 1);
+                    wait_group((int)(k_last >= gs) + (int)(k_last >= gs2));
+                }
+                uint32_t va[32], vb[32];
+                bool fix = false;
+                if (!(xmode & 1)) {
+                    fix = load_block(kbA, va);
+                    if (kbB >= 0) fix |= load_block(kbB, vb);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) va[q] = vb[q] = 0u;
+                }
+                // the A slots are waited for only now: the barrier probe overlaps the shared-memory loads in flight.
+                // The MMAs retire in order: once the later slot of the pair is free, so is the earlier one.
+                const int g_last = kbB >= 0 ? gA + 1 : gA;
+                if (g_last >= kASlots) {
+                    mbar_wait(a_empty + 8 * (g_last & (kASlots - 1)), ((g_last >> 3) - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                TS_DBG((tid & 127) == 0, 12, gA);
+                if (__any_sync(0xffffffffu, fix)) {
+                    fix_block(kbA, va);
+                    if (kbB >= 0) fix_block(kbB, vb);
+                }
+                __syncwarp();
+                TS_DBG((tid & 127) == 0, 2, gA);
+                if (!(xmode & 2)) {
+                    TS_STTM_X32(t_lane + (gA & (kASlots - 1)) * 32, va);
+                    if (kbB >= 0) TS_STTM_X32(t_lane + ((gA + 1) & (kASlots - 1)) * 32, vb);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                } else if (va[0] == 0x12345u && vb[3] == 0x777u) {
+                    y[0] = 1.f;      // keep the loads alive
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(a_full + 8 * (gA & (kASlots - 1)));
+                    if (kbB >= 0) mbar_arrive(a_full + 8 * ((gA + 1) & (kASlots - 1)));
+                }
+                TS_DBG((tid & 127) == 0, 3, gA);
+            }
+            gbase += nact;
+            release_below(ngroups);
+            __syncwarp();
+            if (lane == 0 && !(xmode & 64)) mbar_arrive(lidx_empty + 8 * ib);
+        }
+    } else if (warp < kWarpMma) {
+        // ------------------------------------------------------------------ epilogue (warps 0..3)
+        const int q = warp & 3;                                  // TMEM lane quarter this warp may access
+        float acc_s[COUT / 16], acc_q[COUT / 16];                // running per-channel sum / sum of squares (BatchNorm)
+#pragma unroll
+        for (int i = 0; i < COUT / 16; ++i) acc_s[i] = acc_q[i] = 0.f;
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const int ab = it & 1;
+            mbar_wait(acc_full + 8 * ab, (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = t * kTileM + q * 32 + lane;          // TMEM lane = tile row
+            // row of y this tile row is written to (class-sorted dgrad launches scatter back to canonical rows)
+            const int orow = (out_rows && row < n_out) ? __ldg(out_rows + row) : row;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * COUT;
+#pragma unroll
+            for (int n0 = 0; n0 < COUT; n0 += 16) {
+                uint32_t v[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr + n0));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + n0 + j) : 0.f);
+                if (row < n_out && !(xmode & 16)) {
+                    if (addend) {
+                        const float4 *ad = (const float4 *)(addend + (size_t)orow * COUT + n0);
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            const float4 a4 = __ldg(ad + qq);
+                            o[4 * qq] += a4.x; o[4 * qq + 1] += a4.y; o[4 * qq + 2] += a4.z; o[4 * qq + 3] += a4.w;
+                        }
+                    }
+                    float4 *dst = (float4 *)(y + (size_t)orow * COUT + n0);
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) dst[qq] = make_float4(o[4 * qq], o[4 * qq + 1], o[4 * qq + 2], o[4 * qq + 3]);
+                }
+                if (bn_sums) {
+                    float sq[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        o[j] = row < n_out ? o[j] : 0.f;
+                        sq[j] = o[j] * o[j];
+                    }
+                    acc_s[n0 / 16] += warp_colsum16(o, lane);
+                    acc_q[n0 / 16] += warp_colsum16(sq, lane);
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + 8 * ab);
+        }
+        if (bn_sums && !(lane & 1)) {
+            // lane l (even) owns column n0 + ((l >> 1) & 15); one fp64 atomic per CTA-warp and channel
+            const int col = (lane >> 1) & 15;
+#pragma unroll
+            for (int i = 0; i < COUT / 16; ++i) {
+                atomicAdd(bn_sums + i * 16 + col, (double)acc_s[i]);
+                atomicAdd(bn_sums + COUT + i * 16 + col, (double)acc_q[i]);
+            }
+        }
+    } else if (warp == kWarpMma) {
+        // ------------------------------------------------------------------ MMA issuer, software-pipelined inside the warp:
+        // while lane 0 issues the MMAs of pair p, lanes 1-3 already wait on the barriers of pair p+1 (a try_wait costs
+        // ~100 cycles even when the phase is long complete, the issue of 8 MMAs + commits ~300: serialised, the single
+        // issuing thread was the bottleneck of the small-N layers).  All lanes walk the same pair sequence.
+        constexpr uint32_t idesc = make_idesc_bf16(kTileM, COUT);
+        if (BRES) mbar_wait(b_full, 0);
+        struct Pair { int valid, gA, n, kbA, kbB, first, last, it; };
+        int g_t = blockIdx.x - (int)gridDim.x, g_it = -1, g_j = 0, g_gbase = 0, g_nact = 0;
+        unsigned long long g_cm = 0ull;
+        uint32_t g_om_next = load_om(blockIdx.x);
+        auto next_pair = [&]() -> Pair {
+            Pair P;
+            P.valid = 0; P.gA = 0; P.n = 0; P.kbA = 0; P.kbB = -1; P.first = 0; P.last = 0; P.it = 0;
+            int first = 0;
+            if (!g_cm) {
+                g_t += gridDim.x;
+                ++g_it;
+                if (g_t >= num_tiles) return P;
+                g_gbase += g_nact;
+                const uint32_t om = g_om_next;
+                g_om_next = load_om(g_t + gridDim.x);
+                g_cm = kb_mask_from(om);
+                g_nact = __popcll(g_cm);
+                g_j = 0;
+                first = 1;
+            }
+            P.valid = 1;
+            P.kbA = __ffsll((long long)g_cm) - 1;
+            g_cm &= g_cm - 1;
+            if (g_cm) {
+                P.kbB = __ffsll((long long)g_cm) - 1;
+                g_cm &= g_cm - 1;
+            }
+            P.n = P.kbB >= 0 ? 2 : 1;
+            P.gA = g_gbase + g_j;
+            g_j += 2;
+            P.first = first;
+            P.last = g_cm == 0ull;
+            P.it = g_it;
+            return P;
+        };
+        auto wait_pair = [&](const Pair &P) {      // lanes 1..3 (and 4 for the second weight stage), each on its own barrier
+            if (!P.valid) return;
+            if (lane == 1) {
+                if (P.first && (P.it >> 1) > 0) mbar_wait(acc_empty + 8 * (P.it & 1), ((P.it >> 1) - 1) & 1);   // epilogue has drained this accumulator
+                mbar_wait(a_full + 8 * (P.gA & (kASlots - 1)), (P.gA >> 3) & 1);
+            } else if (lane == 2) {
+                if (P.n == 2) mbar_wait(a_full + 8 * ((P.gA + 1) & (kASlots - 1)), ((P.gA + 1) >> 3) & 1);
+            } else if (!BRES && lane == 3) {
+                mbar_wait(b_full + 8 * (P.gA % SB), (P.gA / SB) & 1);
+            } else if (!BRES && lane == 4) {
+                if (P.n == 2) mbar_wait(b_full + 8 * ((P.gA + 1) % SB), ((P.gA + 1) / SB) & 1);
+            }
+        };
+        Pair cur = next_pair();
+        wait_pair(cur);
+        Pair nxt = next_pair();
+        uint32_t accumulate = 0;
+        while (cur.valid) {
+            __syncwarp();                                   // the barriers of `cur` have been observed by lanes 1-4
+            if (elect_one()) {                              // (= lane 0; ELECT keeps the descriptors in uniform registers)
+                TS_DBG(true, 4, cur.gA);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + (cur.it & 1) * COUT;
+                if (cur.first) accumulate = 0;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    if (i < cur.n) {
+                        const int g = cur.gA + i, kb = i ? cur.kbB : cur.kbA;
+                        const int slot = g & (kASlots - 1), stage = BRES ? kb : g % SB;
+                        const uint64_t bd0 = make_desc_k_sw128(base + stage * C::kBStage);
+                        const uint32_t a0 = tmem_base + kACol0 + slot * 32;
+                        if (!(xmode & 4)) {
+                            umma_bf16_ts(d_tmem, a0, bd0, idesc, accumulate);
+#pragma unroll
+                            for (int jj = 1; jj < 4; ++jj) umma_bf16_ts(d_tmem, a0 + 8 * jj, bd0 + 2 * jj, idesc, 1u);   // K = 16: 8 columns / 32 bytes
+                        }
+                        accumulate = 1u;
+                        umma_commit(a_empty + 8 * slot);
+                        if (!BRES) umma_commit(b_empty + 8 * stage);
+                    }
+                }
+                if (cur.last) umma_commit(acc_full + 8 * (cur.it & 1));
+                TS_DBG(true, 5, cur.gA);
+            } else {
+                wait_pair(nxt);
+            }
+            cur = nxt;
+            nxt = next_pair();
+        }
+        __syncwarp();
+    } else if (warp == kWarpLoader || warp == kWarpLoader2) {
+        // ------------------------------------------------------------------ loaders: table slice + row slabs, up to NB groups ahead.
+        // The two warps take alternate batches of 32 rows; a lane copies whole rows (ascending row ids: neighbouring lanes
+        // read neighbouring rows).
+        constexpr int P = C::kRowBytes / 16;               // 16-byte pieces per row
+        const int L = warp == kWarpLoader ? 0 : 1;
+        constexpr int NBAT = kMaxBatches / 2;
+        // the row list of unit u+1 is fetched while the copies of unit u are issued (a list read is two dependent L2 round trips)
+        int ids_n[NBAT], R_n = 0;
+        auto fetch_unit = [&](int t, int grp) {
+            if (t < num_tiles) {
+                R_n = __ldg(pcnt + (size_t)t * ngroups + grp);
+                const int *rows = prow + ((size_t)t * ngroups + grp) * cap;
+#pragma unroll
+                for (int i = 0; i < NBAT; ++i) {
+                    const int r = (2 * i + L) * 32 + lane;
+                    ids_n[i] = r < R_n ? __ldg(rows + r) : -1;
+                }
+            }
+        };
+        fetch_unit(blockIdx.x, 0);
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const int ib = it & 1;
+            if (L == 0 && lane == 0 && !(xmode & 64)) {
+                if (it >= 2) mbar_wait(lidx_empty + 8 * ib, ((it >> 1) - 1) & 1);
+                const uint32_t bytes = (uint32_t)kvol * (kTileM * 2);
+                mbar_arrive_expect_tx(lidx_full + 8 * ib, bytes);
+                bulk_copy_g2s(lidx_base + ib * kLidxBytes, lidx + (size_t)t * kvol * kTileM, bytes, lidx_full + 8 * ib);
+            }
+            __syncwarp();
+            for (int grp = 0; grp < ngroups && !(xmode & 32); ++grp) {
+                const int u = it * ngroups + grp, buf = u % NB, use = u / NB;
+                TS_DBG(L == 0 && lane == 0, 7, u);
+                int ids[NBAT];
+#pragma unroll
+                for (int i = 0; i < NBAT; ++i) ids[i] = ids_n[i];
+                const int R = R_n;
+                if (grp + 1 < ngroups) fetch_unit(t, grp + 1);
+                else fetch_unit(t + gridDim.x, 0);
+                if (use > 0) mbar_wait(slab_empty + 8 * buf, (use - 1) & 1);
+                if (dbg && blockIdx.x == 0 && L == 0 && lane == 0 && u < 256) dbg[11 * 256 + u] = R;
+                TS_DBG(L == 0 && lane == 0, 8, u);
+                const uint32_t dst0 = slab_base + buf * C::kSlab + lane * C::kStride;
+#pragma unroll
+                for (int i = 0; i < NBAT; ++i) {
+                    if (ids[i] >= 0 && !(xmode & 8)) {
+                        const char *src = (const char *)xb + (size_t)ids[i] * C::kRowBytes;
+                        const uint32_t dst = dst0 + (2 * i + L) * 32 * C::kStride;
+#pragma unroll
+                        for (int jj = 0; jj < P; ++jj) cp_async_16(dst + 16 * jj, src + 16 * jj);
+                    }
+                }
+                cp_async_arrive_noinc(slab_full + 8 * buf);
+                TS_DBG(L == 0 && lane == 0, 9, u);
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    } else {
+        // ------------------------------------------------------------------ weight producer
+        if (lane == 0) {
+            if (BRES) {
+                // every K block once, resident for the lifetime of the CTA
+                mbar_arrive_expect_tx(b_full, (uint32_t)nkb * C::kBStage);
+                for (int kb = 0; kb < nkb; ++kb) tma_load_2d(base + kb * C::kBStage, &map_w, kb * 64, 0, b_full);
+            } else {
+                int g = 0;
+                for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                    for (unsigned long long cm = kb_mask_of(t); cm; cm &= cm - 1, ++g) {
+                        const int kb = __ffsll((long long)cm) - 1;
+                        const int stage = g % SB, use = g / SB;
+                        if (use > 0) mbar_wait(b_empty + 8 * stage, (use - 1) & 1);
+                        TS_DBG(true, 13, g);
+                        mbar_arrive_expect_tx(b_full + 8 * stage, C::kBStage);
+                        tma_load_2d(base + stage * C::kBStage, &map_w, kb * 64, 0, b_full + 8 * stage);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == kWarpMma) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Plan: one CTA (128 threads = the tile's rows) per (tile, offset group).  The distinct neighbour rows of the group are
+// found with a shared-memory bitmap over the window [min row, min row + 32768): set bits, prefix popcount = slot of
+// every row in ascending row order (sorted lists keep the slab fill coalesced).  Rows outside the window or beyond the
+// slab capacity are flagged kLidxGlobal and read from global memory by the conv kernel.  Deterministic.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kPlanWords = kPlanWindow / 32;       // 1024
+__global__ void __launch_bounds__(128) tile_plan_kernel(const int *__restrict__ nbr, int n_out, int kvol, int ngroups, int cap,
+                                                        uint16_t *__restrict__ lidx, int *__restrict__ prow, int *__restrict__ pcnt) {
+    __shared__ uint32_t bits[kPlanWords];
+    __shared__ uint16_t pref[kPlanWords];
+    __shared__ int red[4];
+    __shared__ int wsum[4];
+    const int tile = blockIdx.x / ngroups, grp = blockIdx.x % ngroups;
+    const int gs = kvol / ngroups;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row = tile * kTileM + tid;
+    int v[9];
+    int mn = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        v[j] = -1;
+        if (j < gs && row < n_out) v[j] = __ldg(nbr + (size_t)(grp * gs + j) * n_out + row);
+        if (v[j] >= 0) mn = min(mn, v[j]);
+    }
+    for (int w = tid; w < kPlanWords; w += 128) bits[w] = 0u;
+    for (int o = 16; o; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    if (lane == 0) red[warp] = mn;
+    __syncthreads();
+    const int base = min(min(red[0], red[1]), min(red[2], red[3]));
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        if (v[j] >= 0) {
+            const unsigned d = (unsigned)(v[j] - base);
+            if (d < (unsigned)kPlanWindow) atomicOr(&bits[d >> 5], 1u << (d & 31));
+        }
+    }
+    __syncthreads();
+    // exclusive prefix of popcounts over the 1024 words: 8 consecutive words per thread
+    int cnt8[8], s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        cnt8[j] = s;
+        s += __popc(bits[tid * 8 + j]);
+    }
+    int incl = s;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int nb = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += nb;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += wsum[w];
+    const int excl = woff + incl - s;
+    const int total = wsum[0] + wsum[1] + wsum[2] + wsum[3];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pref[tid * 8 + j] = (uint16_t)min(excl + cnt8[j], 0xFFFF);
+    // the row list: every set bit, in ascending order
+    int *rows = prow + ((size_t)tile * ngroups + grp) * cap;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        uint32_t wbits = bits[tid * 8 + j];
+        int slot = excl + cnt8[j];
+        while (wbits) {
+            const int b = __ffs(wbits) - 1;
+            wbits &= wbits - 1;
+            if (slot < cap) rows[slot] = base + (tid * 8 + j) * 32 + b;
+            ++slot;
+        }
+    }
+    if (tid == 0) pcnt[(size_t)tile * ngroups + grp] = min(total, cap);
+    __syncthreads();
+    uint16_t *lt = lidx + ((size_t)tile * kvol + (size_t)grp * gs) * kTileM + tid;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        if (j < gs) {
+            uint32_t li = kLidxNone;
+            if (v[j] >= 0) {
+                const unsigned d = (unsigned)(v[j] - base);
+                li = kLidxGlobal;
+                if (d < (unsigned)kPlanWindow) {
+                    const int slot = (int)pref[d >> 5] + __popc(bits[d >> 5] & ((1u << (d & 31)) - 1u));
+                    if (slot < cap) li = (uint32_t)slot;
+                }
+            }
+            lt[(size_t)j * kTileM] = (uint16_t)li;
+        }
+    }
+}
+
+template <int CIN, int COUT>
+int launch_ts(const __nv_bfloat16 *xb, const int32_t *nbr, int n_out, int kvol, const TilePlan &plan, const __nv_bfloat16 *wb,
+              const float *bias, const float *addend, float *y, const int32_t *out_rows, const uint32_t *tile_masks, double *bn_sums,
+              cudaStream_t st) {
+    using C = TsCfg<CIN, COUT>;
+    if (plan.cap > C::kCap) {
+        toda_set_error("conv_ts_fwd: plan capacity %d exceeds the slab capacity %d of Cin=%d", plan.cap, C::kCap, CIN);
+        return TODA_ERR_INVALID;
+    }
+    CUtensorMap map_w;
+    if (int rc = conv_tma_make_map(&map_w, wb, (uint64_t)COUT, (uint64_t)kvol * CIN, (uint32_t)COUT, 64)) return rc;
+    const int num_tiles = ceil_div(n_out, kTileM);
+    const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+    static bool attr_set = false;      // per <CIN, COUT> instantiation
+    if (!attr_set) {
+        TODA_CUDA_OK(cudaFuncSetAttribute(conv_ts_fwd_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
+        attr_set = true;
+    }
+    conv_ts_fwd_kernel<CIN, COUT><<<grid, kThreads, C::kSmem, st>>>(xb, nbr, n_out, kvol, plan.lidx, plan.rows, plan.cnt, plan.ngroups,
+                                                                   plan.cap, map_w, bias, addend, y, out_rows, tile_masks, bn_sums,
+                                                                   num_tiles, conv_tc_debug_timeline(), conv_tc_debug_mode());
+    TODA_LAUNCH_OK();
+    return TODA_OK;
+}
+
+}  // namespace
+
+int conv_ts_slab_capacity(int cin) {
+    switch (cin <= 16 ? 16 : cin) {
+        case 16: return TsCfg<16, 16>::kCap;
+        case 32: return TsCfg<32, 32>::kCap;
+        case 64: return TsCfg<64, 64>::kCap;
+        case 128: return TsCfg<128, 128>::kCap;
+    }
+    return 0;
+}
+
+bool conv_ts_supported(int cin, int cout, int kvol, const TilePlan *plan) {
+    if (!plan || !plan->lidx || !plan->rows || !plan->cnt) return false;
+    if (plan->ngroups < 1 || plan->ngroups > 3 || kvol % plan->ngroups != 0 || kvol / plan->ngroups > 9 || kvol > kMaxKvol) return false;
+    const int cp = cin <= 16 ? 16 : cin;
+    if (!(cp == 16 || cp == 32 || cp == 64 || cp == 128)) return false;
+    if (!(cout == 16 || cout == 32 || cout == 64 || cout == 128)) return false;
+    return plan->cap >= 1 && plan->cap <= conv_ts_slab_capacity(cp);
+}
+
+// xb: bf16 [n_in][cin], wb: bf16 [cout][kvol*cin]; cin, cout in {16,32,64,128}
+int conv_ts_fwd(const void *xb, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const TilePlan &plan, const void *wb,
+                int cout, const float *bias, const float *addend, float *y, const int32_t *out_rows, const uint32_t *tile_masks,
+                double *bn_sums, cudaStream_t st) {
+    (void)n_in;
+    const __nv_bfloat16 *x = (const __nv_bfloat16 *)xb, *w = (const __nv_bfloat16 *)wb;
+#define CASE_CO(CI)                                                                                                          \
+    switch (cout) {                                                                                                          \
+        case 16: return launch_ts<CI, 16>(x, nbr, n_out, kvol, plan, w, bias, addend, y, out_rows, tile_masks, bn_sums, st);   \
+        case 32: return launch_ts<CI, 32>(x, nbr, n_out, kvol, plan, w, bias, addend, y, out_rows, tile_masks, bn_sums, st);   \
+        case 64: return launch_ts<CI, 64>(x, nbr, n_out, kvol, plan, w, bias, addend, y, out_rows, tile_masks, bn_sums, st);   \
+        case 128: return launch_ts<CI, 128>(x, nbr, n_out, kvol, plan, w, bias, addend, y, out_rows, tile_masks, bn_sums, st); \
+    }                                                                                                                        \
+    break;
+    switch (cin) {
+        case 16: CASE_CO(16)
+        case 32: CASE_CO(32)
+        case 64: CASE_CO(64)
+        case 128: CASE_CO(128)
+    }
+#undef CASE_CO
+    toda_set_error("conv_ts_fwd: unsupported cin=%d cout=%d", cin, cout);
+    return TODA_ERR_UNSUPPORTED;
+}
+
+extern "C" int toda_tile_plan_capacity(int channels) { return conv_ts_slab_capacity(channels); }
+
+extern "C" int toda_table_tile_plan(const int32_t *nbr, int n_out, int kvol, int ngroups, int cap, uint16_t *lidx, int32_t *rows,
+                                    int32_t *cnt, void *stream) {
+    TODA_CHECK_ARG(n_out >= 0 && kvol > 0 && kvol <= kMaxKvol, "table_tile_plan: bad sizes n_out=%d kvol=%d", n_out, kvol);
+    TODA_CHECK_ARG(ngroups >= 1 && ngroups <= 3 && kvol % ngroups == 0 && kvol / ngroups <= 9, "table_tile_plan: bad groups %d", ngroups);
+    TODA_CHECK_ARG(cap >= 1 && cap <= 32 * kMaxBatches, "table_tile_plan: bad capacity %d", cap);
+    if (n_out == 0) return TODA_OK;
+    TODA_CHECK_ARG(nbr && lidx && rows && cnt, "table_tile_plan: null pointer");
+    const int num_tiles = ceil_div(n_out, kTileM);
+    tile_plan_kernel<<<num_tiles * ngroups, 128, 0, (cudaStream_t)stream>>>(nbr, n_out, kvol, ngroups, cap, lidx, rows, cnt);
+    TODA_LAUNCH_OK();
+    return TODA_OK;
+}

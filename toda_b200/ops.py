@@ -370,17 +370,57 @@ class Rulebook:
     nbr_bwd_sorted: Optional[torch.Tensor] = None
     dgrad_tile_masks: Optional[torch.Tensor] = None   # per 128-row tile of nbr_bwd_sorted: which offsets hold a neighbour
     tile_masks: Optional[torch.Tensor] = None         # the same for nbr_fwd (forward; SubM dgrad walks the same table)
+    plan: Optional["TilePlan"] = None                 # row-cache plan of nbr_fwd (forward; SubM dgrad)
+    dgrad_plan: Optional["TilePlan"] = None           # row-cache plan of the strided dgrad table (nbr_bwd_sorted / nbr_bwd)
 
     @property
     def kvol(self):
         return self.ksize[0] * self.ksize[1] * self.ksize[2]
 
 
+@dataclass
+class TilePlan:
+    """Row-cache plan of one neighbour table (toda_table_tile_plan): per 128-row tile and kz-group of offsets the distinct
+    input rows, and the table rewritten as 16-bit slots into those lists."""
+    lidx: torch.Tensor      # int16 (tiles, kvol, 128)
+    rows: torch.Tensor      # int32 (tiles, ngroups, cap)
+    cnt: torch.Tensor       # int32 (tiles, ngroups)
+    ngroups: int
+    cap: int
+
+    def tensors(self):
+        return [self.lidx, self.rows, self.cnt]
+
+
+def table_tile_plan(nbr, ksize, channels):
+    """Plan for the convolutions that gather `channels`-wide rows through `nbr` (None when the shape is not covered)."""
+    kvol, n = nbr.shape
+    ngroups = int(ksize[0])
+    if n == 0 or kvol > 27 or ngroups > 3 or kvol % ngroups or kvol // ngroups > 9 or not channels:
+        return None
+    L = _C.lib()
+    cap = L.toda_tile_plan_capacity(int(channels))
+    if cap <= 0:
+        return None
+    tiles = (n + 127) // 128
+    dev = nbr.device
+    lidx = torch.empty((tiles, kvol, 128), dtype=torch.int16, device=dev)
+    rows = torch.empty((tiles, ngroups, cap), dtype=torch.int32, device=dev)
+    cnt = torch.empty((tiles, ngroups), dtype=torch.int32, device=dev)
+    with _timed("tile_plan", n=n, kvol=kvol):
+        _C.check(L.toda_table_tile_plan(_p(nbr), n, kvol, ngroups, cap, _p(lidx), _p(rows), _p(cnt), _stream()),
+                 "toda_table_tile_plan")
+    _count(1)
+    return TilePlan(lidx, rows, cnt, ngroups, cap)
+
+
 def conv_out_size(in_size, k, s, p):
     return (in_size + 2 * p - (k - 1) - 1) // s + 1
 
 
-def rulebook_subm(index: OccupancyIndex, ksize):
+def rulebook_subm(index: OccupancyIndex, ksize, channels=None):
+    """channels: width of the rows gathered through this table (max of Cin for forward / Cout for dgrad): sizes the
+    row-cache plan of the tensor-core kernel; None = no plan."""
     index.ensure_live()
     n = index.n
     kvol = ksize[0] * ksize[1] * ksize[2]
@@ -394,11 +434,13 @@ def rulebook_subm(index: OccupancyIndex, ksize):
     # even in raster order a 128-row tile often has no neighbour at all under whole groups of offsets (e.g. no dz = -1 /
     # +1 neighbours on flat ground): 45 % of the K chunks at stride 1, 15-20 % deeper; the kernel skips them
     rb.tile_masks = table_tile_masks(nbr) if n > 0 else None
+    rb.plan = table_tile_plan(nbr, ksize, channels) if _TILE_PLANS else None
     return rb
 
 
-def rulebook_sparse(index_in: OccupancyIndex, ksize, stride, padding, tag):
-    """Builds the output index (kept alive in the returned tuple) and both tables."""
+def rulebook_sparse(index_in: OccupancyIndex, ksize, stride, padding, tag, cin=None, cout=None):
+    """Builds the output index (kept alive in the returned tuple) and both tables.  cin / cout size the row-cache plans
+    (forward gathers Cin-wide rows through nbr_fwd, dgrad Cout-wide rows through nbr_bwd)."""
     index_in.ensure_live()
     out_shape = [conv_out_size(index_in.shape[a], ksize[a], stride[a], padding[a]) for a in range(3)]
     index_out = OccupancyIndex(index_in.batch, out_shape, index_in.buf.device, tag)
@@ -426,7 +468,15 @@ def rulebook_sparse(index_in: OccupancyIndex, ksize, stride, padding, tag):
     rb.dgrad_order, rb.nbr_bwd_sorted = _dgrad_parity_order(index_in.coords, nbr_bwd, stride, padding)
     if rb.dgrad_order is not None:
         rb.dgrad_tile_masks = table_tile_masks(rb.nbr_bwd_sorted)
+    if _TILE_PLANS:
+        rb.plan = table_tile_plan(nbr_fwd, ksize, cin)
+        rb.dgrad_plan = table_tile_plan(rb.nbr_bwd_sorted if rb.dgrad_order is not None else nbr_bwd, ksize, cout)
     return rb, index_out
+
+
+# TODA_TILE_PLANS=0 keeps the round-1 tensor-core kernels (no row cache) for A/B measurements
+import os as _os
+_TILE_PLANS = _os.environ.get("TODA_TILE_PLANS", "1") != "0"
 
 
 def table_tile_masks(nbr):
@@ -493,18 +543,39 @@ def _bf16_shadow_of(t):
 
 
 def _conv_call(x, xb, cin, nbr, n_out, kvol, w, cout, bias, precision, what="conv_fwd", rb=None, bn_sums=None, y=None,
-               out_rows=None, tile_masks=None):
+               out_rows=None, tile_masks=None, plan=None, addend=None):
+    """addend (optional, (n_out, cout) fp32): added to the result in the kernel's epilogue; only with a usable plan
+    (see conv_plan_usable), otherwise the caller adds it."""
     if y is None:
         y = torch.empty((n_out, cout), dtype=torch.float32, device=x.device)
     L = _C.lib()
     ws_bytes = L.toda_spconv_fwd_workspace_bytes(x.shape[0], cin, cout, kvol, precision)
     ws = _workspace("conv", ws_bytes, x.device) if ws_bytes else None
+    if precision != CONV_BF16:
+        plan = None
     with _timed(what, n_in=x.shape[0], n_out=n_out, cin=cin, cout=cout, kvol=kvol, precision=precision, rb=id(rb)):
-        _C.check(L.toda_spconv_fwd(_p(x), _p(xb), x.shape[0], cin, _p(nbr), n_out, kvol, _p(w), cout, _p(bias), _p(y),
-                                   _p(out_rows), _p(tile_masks), _p(bn_sums), precision, _p(ws), ws.numel() if ws is not None else 0,
-                                   _stream()), "toda_spconv_fwd")
+        if plan is None:
+            assert addend is None
+            _C.check(L.toda_spconv_fwd(_p(x), _p(xb), x.shape[0], cin, _p(nbr), n_out, kvol, _p(w), cout, _p(bias), _p(y),
+                                       _p(out_rows), _p(tile_masks), _p(bn_sums), precision, _p(ws), ws.numel() if ws is not None else 0,
+                                       _stream()), "toda_spconv_fwd")
+        else:
+            _C.check(L.toda_spconv_fwd_plan(_p(x), _p(xb), x.shape[0], cin, _p(nbr), n_out, kvol, _p(w), cout, _p(bias),
+                                            _p(addend), _p(y), _p(out_rows), _p(tile_masks), _p(plan.lidx), _p(plan.rows),
+                                            _p(plan.cnt), plan.ngroups, plan.cap, _p(bn_sums), precision, _p(ws),
+                                            ws.numel() if ws is not None else 0, _stream()), "toda_spconv_fwd_plan")
     _count(1)
     return y
+
+
+def conv_plan_usable(plan, cin, cout, kvol, precision):
+    """True when toda_spconv_fwd_plan will run the row-cache kernel for this call (and can therefore fuse an addend)."""
+    if plan is None or precision != CONV_BF16 or _os.environ.get("TODA_TC_FEED", "ts")[:1] in ("c",) or \
+            _os.environ.get("TODA_TC_FEED", "ts")[:2] == "tm":
+        return False
+    cp = max(16, cin)
+    return (cp in (16, 32, 64, 128) and cout in (16, 32, 64, 128) and kvol <= 27
+            and plan.cap <= _C.lib().toda_tile_plan_capacity(cp))
 
 
 def _conv_forward_impl(x, x_bf16, weight, bias, rb, precision, want_stats):
@@ -522,7 +593,7 @@ def _conv_forward_impl(x, x_bf16, weight, bias, rb, precision, want_stats):
     if want_stats and rb.n_out > 0 and _C.lib().toda_spconv_uses_tensor_cores(cin, cout, rb.kvol, precision):
         sums = torch.empty((2 * cout,), dtype=torch.float64, device=x.device)
     y = _conv_call(x, x_bf16, cin, rb.nbr_fwd, rb.n_out, rb.kvol, w, cout, b, precision, "conv_fwd", rb, sums,
-                   tile_masks=rb.tile_masks)
+                   tile_masks=rb.tile_masks, plan=rb.plan)
     return y, sums, x, weight, x_bf16
 
 
@@ -535,13 +606,14 @@ def _conv_backward_impl(dy, dyb, x, weight, xb, rb, precision, need_dx, need_dw,
         wt = _repack(weight, True, rb.subm)
         if rb.subm:
             dx = _conv_call(dy, dyb, cout, rb.nbr_fwd, rb.n_in, rb.kvol, wt, cin, None, precision, "conv_dgrad", rb,
-                            tile_masks=rb.tile_masks)
+                            tile_masks=rb.tile_masks, plan=rb.plan)
         elif rb.dgrad_order is None:
-            dx = _conv_call(dy, dyb, cout, rb.nbr_bwd, rb.n_in, rb.kvol, wt, cin, None, precision, "conv_dgrad", rb)
+            dx = _conv_call(dy, dyb, cout, rb.nbr_bwd, rb.n_in, rb.kvol, wt, cin, None, precision, "conv_dgrad", rb,
+                            plan=rb.dgrad_plan)
         else:
             # strided conv: rows in parity-class order (empty K blocks are skipped), written back to canonical rows
             dx = _conv_call(dy, dyb, cout, rb.nbr_bwd_sorted, rb.n_in, rb.kvol, wt, cin, None, precision, "conv_dgrad",
-                            rb, out_rows=rb.dgrad_order, tile_masks=rb.dgrad_tile_masks)
+                            rb, out_rows=rb.dgrad_order, tile_masks=rb.dgrad_tile_masks, plan=rb.dgrad_plan)
     if need_dw:
         dw = torch.empty_like(weight)
         ws_bytes = L.toda_spconv_wgrad_workspace_bytes(rb.n_in, rb.n_out, rb.kvol, cin, cout, precision)

@@ -221,10 +221,11 @@ class SparseConvolution(SparseModule):
             if geom_ok:
                 return rb, index_out
         if self.subm:
-            rb = ops.rulebook_subm(x._index, self.kernel_size)
+            rb = ops.rulebook_subm(x._index, self.kernel_size, channels=max(self.in_channels, self.out_channels))
             index_out = x._index
         else:
-            rb, index_out = ops.rulebook_sparse(x._index, self.kernel_size, self.stride, self.padding, ("out", str(key)))
+            rb, index_out = ops.rulebook_sparse(x._index, self.kernel_size, self.stride, self.padding, ("out", str(key)),
+                                                cin=self.in_channels, cout=self.out_channels)
         if key is not None:
             x.indice_dict[key] = (rb, index_out)
         return rb, index_out
@@ -264,6 +265,9 @@ class GeometryPlan:
                 out.append(index_out.frame_counts)
             if rb.dgrad_order is not None:
                 out += [rb.dgrad_order, rb.nbr_bwd_sorted, rb.dgrad_tile_masks]
+            for pl in (rb.plan, rb.dgrad_plan):
+                if pl is not None:
+                    out += pl.tensors()
         return [t for t in out if t is not None]
 
     def sparse_tensor(self, features, features_bf16=None):
