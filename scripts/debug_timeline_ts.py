@@ -23,8 +23,10 @@ n = rb.n_in
 x = torch.randn(n, cin, device=dev)
 w = torch.randn(cout, 3, 3, 3, cin, device=dev) * 0.1
 L = _C.lib()
-R = 16
+R = 24
 buf = torch.zeros(R * 256, dtype=torch.int64, device=dev)
+L.toda_debug_set_mode.argtypes = [ctypes.c_int]
+L.toda_debug_set_mode(int(os.environ.get('TS_MODE', '0')))
 for _ in range(3): ops.sparse_conv(x, w, None, rb, ops.CONV_BF16)
 L.toda_debug_set_timeline.argtypes = [ctypes.c_void_p]
 L.toda_debug_set_timeline(ctypes.c_void_p(buf.data_ptr()))
@@ -50,8 +52,10 @@ for g in range(g_lo, min(g_hi, 255)):
         continue
     a = [int(t[r, g] - t0) for r in (0, 1, 12, 2, 3)]
     m = [int(t[r, g] - t0) for r in (4, 5)]
-    print("g %3d  gather %8d +%5d +%5d +%5d +%5d = %5d | mma issue %8d +%5d" %
-          (g, a[0], a[1] - a[0], a[2] - a[1], a[3] - a[2], a[4] - a[3], a[4] - a[0], m[0], m[1] - m[0]))
+    wg = 0 if t[16, g] else 4
+    arr = [int(t[16 + wg + i, g] - t0) for i in range(4)]
+    print("g %3d  gather %8d +%5d +%5d +%5d +%5d = %5d | arrivals of the 4 warps %s | mma issue %8d +%5d" %
+          (g, a[0], a[1] - a[0], a[2] - a[1], a[3] - a[2], a[4] - a[3], a[4] - a[0], arr, m[0], m[1] - m[0]))
 print("-- loader per unit u: start | ids+slab_empty | issued | rows")
 for u in range(12, 30):
     print("u %3d  %8d +%5d +%5d  R=%d" % (u, int(t[7, u] - t0), int(t[8, u] - t[7, u]), int(t[9, u] - t[8, u]), int(t[11, u])))

@@ -30,14 +30,15 @@ constexpr int kMaxKvol = 27;
 constexpr int kLidxBytes = 7168;                  // >= 27 * 128 * 2, 1024-multiple
 constexpr uint32_t kLidxNone = 0xFFFFu;           // no neighbour under this offset
 constexpr uint32_t kLidxGlobal = 0xFFFEu;         // neighbour exists but is not in the slab: read it from global memory
-constexpr int kGatherWarps = 8;
+constexpr int kGatherWarps = 16;                  // four warpgroups; a lone warp issues ~1 instruction per 5 cycles, so throughput comes from warps
 // the warp scheduler favours high warp ids: the latency-critical gather warps get them
 constexpr int kWarpMma = 4, kWarpLoader = 5, kWarpB = 6, kWarpLoader2 = 7, kWarpGather0 = 8;
-constexpr int kThreads = 16 * 32;
-constexpr int kASlots = 8;
-constexpr int kACol0 = 256;
-constexpr int kPlanWindow = 32768;                // row-id window of the plan kernel's bitmap
-constexpr int kMaxBatches = 16;                   // slab capacity <= 512 rows
+constexpr int kThreads = 24 * 32;
+// A ring: pair slots of 2 x 32 TMEM columns (2 x 64 K elements) behind the two accumulators
+// Four slots = one per gather warpgroup: pair gp is produced by warpgroup gp % 4 into slot gp % 4, so every waiter of a slot's
+// barriers sees each of its phases in turn (a parity wait by a thread that is two phases behind would pass at once).
+template <int COUT> struct ARing { static constexpr int kSlots = 4; static constexpr int kCol0 = 256; };
+constexpr int kPlanWindow = 32768;                // block-id window of the plan kernel's bitmap
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -56,7 +57,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity), "r"(0x4000u)
             : "memory");
-        if (!done && ++spins > (1u << 20)) __trap();   // a lost arrival must not hang the GPU box
+        if (!done && ++spins > (1u << 20)) {           // a lost arrival must not hang the GPU box
+            printf("conv_ts: mbarrier timeout smem=0x%x parity=%u block=%d warp=%d lane=%d\n", bar, parity, (int)blockIdx.x, (int)(threadIdx.x >> 5), (int)(threadIdx.x & 31));
+            __trap();
+        }
     }
 }
 __device__ __forceinline__ bool elect_one() {
@@ -127,10 +131,13 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
 
 template <int CIN, int COUT> struct TsCfg {
     static constexpr int kRowBytes = CIN * 2;
-    static constexpr int kStride = kRowBytes + 16;             // (stride / 16) odd: 8 consecutive slots hit 8 different 16-byte bank groups
+    static constexpr int kRB = kRowBytes < 128 ? kRowBytes : 128;   // bytes of a row inside one swizzled slab half
+    static constexpr int kHalves = kRowBytes / kRB;                  // 2 for 256-byte rows (two 128-byte column halves)
     static constexpr int kNB = CIN == 128 ? 2 : 3;             // slab buffers (one per offset group in flight)
-    static constexpr int kSlab = CIN == 128 ? 65536 : (CIN == 64 ? 40960 : (CIN == 32 ? 32768 : 24576));
-    static constexpr int kCap = kSlab / kStride - 1;           // 239 / 283 / 408 / 511 rows + the all-zero row at slot `cap`
+    // a slab caches 16-row BLOCKS of x (rows 16 b .. 16 b + 15), each brought in by one TMA box copy
+    static constexpr int kCap = CIN == 128 ? 16 : (CIN == 64 ? 20 : 32);   // blocks per slab (<= 32: one loader lane per block)
+    static constexpr int kHalfSlab = kCap * 16 * kRB;
+    static constexpr int kSlab = kHalfSlab * kHalves;          // 16 / 32 / 40 / 64 KB
     static constexpr int kBStage = COUT * 128;                 // [COUT rows][64 bf16]
     static constexpr int kNkbMax = (kMaxKvol * CIN + 63) / 64;
     // small layers keep ALL their weights in shared memory for the lifetime of the (persistent) CTA: no per-tile re-fetch
@@ -139,13 +146,16 @@ template <int CIN, int COUT> struct TsCfg {
     static constexpr int kSB = kBRes ? kNkbMax : (COUT == 128 ? 4 : (COUT == 64 ? 6 : 8));
     static constexpr int kParts = CIN >= 64 ? 1 : 64 / CIN;    // kernel offsets per 64-element K block
     static constexpr int kPV = (CIN >= 64 ? 64 : CIN) / 8;     // 16-byte vectors per part
-    static constexpr int kSmemRaw = 1024 + kSB * kBStage + kNB * kSlab + 2 * kLidxBytes + 512;
+    static constexpr int kSmemRaw = 1024 + kSB * kBStage + kNB * kSlab + 2 * kLidxBytes + 512 + 256;
     // the kernel allocates all 512 TMEM columns: never let two CTAs share an SM (the second would wait in tcgen05.alloc)
     static constexpr int kSmem = kSmemRaw < 120 * 1024 ? 120 * 1024 : kSmemRaw;
-    static_assert(kCap <= 32 * kMaxBatches, "slab capacity");
-    static_assert(2 * COUT <= kACol0, "accumulators overlap the A ring");
+    static_assert(kCap <= 32 && kSlab % 1024 == 0 && kBStage % 1024 == 0, "slab layout");
+    static_assert(2 * COUT <= ARing<COUT>::kCol0 && ARing<COUT>::kCol0 + 64 * ARing<COUT>::kSlots <= 512, "TMEM map");
     static constexpr int kBBars = kBRes ? 1 : kSB;             // resident weights arrive on one barrier, once
     static_assert(kBBars <= 14, "barrier area");
+    // TMA swizzle of a slab row (hardware XORs the 16-byte chunk index with address bits 7..9 / 7..8 / 7): chunk q of slot s
+    // lives at s * kRB + ((q ^ swz(s)) << 4); eight consecutive slots then hit eight different 16-byte bank groups
+    __device__ static __forceinline__ uint32_t swz(uint32_t s) { return kRB == 128 ? (s & 7u) : (kRB == 64 ? ((s >> 1) & 3u) : ((s >> 2) & 1u)); }
 };
 
 #define TS_STTM_X32(addr, v)                                                                                                        \
@@ -165,6 +175,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
                                                                   int n_out, int kvol, const uint16_t *__restrict__ lidx,
                                                                   const int *__restrict__ prow, const int *__restrict__ pcnt,
                                                                   int ngroups, int cap,
+                                                                  const __grid_constant__ CUtensorMap map_x /*[n_in][CIN] bf16, box 16 rows*/,
                                                                   const __grid_constant__ CUtensorMap map_w /*[COUT][kvol*CIN] bf16*/,
                                                                   const float *__restrict__ bias, const float *__restrict__ addend,
                                                                   float *__restrict__ y, const int *__restrict__ out_rows,
@@ -173,6 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
     using C = TsCfg<CIN, COUT>;
     constexpr int NB = C::kNB, SB = C::kSB, PARTS = C::kParts, PV = C::kPV;
     constexpr bool BRES = C::kBRes;
+    constexpr int kASlots = ARing<COUT>::kSlots, kACol0 = ARing<COUT>::kCol0;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;          // B stages: SWIZZLE_128B tiles need 1024-byte alignment
@@ -185,6 +197,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
     const uint32_t slab_full = bar_base + 384, slab_empty = bar_base + 408;   // 3 + 3
     const uint32_t lidx_full = bar_base + 432, lidx_empty = bar_base + 448;   // 2 + 2
     const uint32_t tmem_slot = bar_base + 464;
+    const uint32_t zero_base = bar_base + 512;               // 256 zero bytes: the row read for a missing neighbour
     volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *)(smem_raw + (tmem_slot - raw));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -224,7 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
             mbar_init(lidx_empty + 8 * b, kGatherWarps);
         }
         for (int b = 0; b < NB; ++b) {
-            mbar_init(slab_full + 8 * b, 64);      // one cp.async-completion arrival per lane of the two loader warps
+            mbar_init(slab_full + 8 * b, 1);       // arrive.expect_tx by the loader; the TMA box copies complete the bytes
             mbar_init(slab_empty + 8 * b, kGatherWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -234,17 +247,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp == kWarpB && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-    if (tid < NB * (C::kRowBytes / 16)) {
-        // the all-zero row of every slab (slot `cap`; the loaders only ever write slots < cap)
-        const int b = tid / (C::kRowBytes / 16), pc = tid % (C::kRowBytes / 16);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(slab_base + b * C::kSlab + cap * C::kStride + pc * 16), "r"(0u) : "memory");
-    }
+    if (tid < 16) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(zero_base + tid * 16), "r"(0u) : "memory");
+    if (warp == kWarpLoader && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot_ptr;
     // development aid (scripts/debug_timeline_ts.py): clock64 samples of CTA 0, 16 rows x 256 entries
+#ifdef TODA_TS_TIMELINE
 #define TS_DBG(cond, rowi, idx) do { if (dbg && blockIdx.x == 0 && (cond) && (idx) < 256) dbg[(rowi) * 256 + (idx)] = clock64(); } while (0)
+#else
+#define TS_DBG(cond, rowi, idx) do { } while (0)
+#endif
 
     if (warp >= kWarpGather0) {
         // ------------------------------------------------------------------ gather warps: thread = tile row = TMEM lane
@@ -253,7 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
         const int wg = (warp - kWarpGather0) >> 2;
         const int row = (warp & 3) * 32 + lane;
         const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kACol0;
-        int gbase = 0, it = 0;                          // gbase: global index of this tile's first active K block
+        int gbase = 0, gpbase = 0, it = 0;              // global index of this tile's first active K block / first pair
         uint32_t om_next = load_om(blockIdx.x);
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int ib = it & 1;
@@ -295,15 +309,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
 #pragma unroll
                 for (int part = 0; part < PARTS; ++part) {
                     const int k = CIN == 128 ? (kb >> 1) : kb * PARTS + part;
-                    const uint32_t half = CIN == 128 ? (uint32_t)(kb & 1) * 128u : 0u;
                     const int grp = (int)(k >= gs) + (int)(k >= gs2);
-                    const uint32_t sl = min(li[part], (uint32_t)cap);
-                    const uint32_t src = slab_base + (uint32_t)((unit0 + grp) % NB) * C::kSlab + sl * C::kStride + half;
+                    const uint32_t sl = li[part];
+                    const bool hit = sl < kLidxGlobal;
+                    const uint32_t buf = slab_base + (uint32_t)((unit0 + grp) % NB) * C::kSlab + (CIN == 128 ? (uint32_t)(kb & 1) * C::kHalfSlab : 0u);
+                    const uint32_t src = hit ? buf + sl * C::kRB : zero_base;
+                    const uint32_t x = hit ? C::swz(sl) : 0u;
 #pragma unroll
                     for (int q = 0; q < PV; ++q)
-                        lds128(src + 16 * q, v[(part * PV + q) * 4], v[(part * PV + q) * 4 + 1], v[(part * PV + q) * 4 + 2],
+                        lds128(src + (((uint32_t)q ^ x) << 4), v[(part * PV + q) * 4], v[(part * PV + q) * 4 + 1], v[(part * PV + q) * 4 + 2],
                                v[(part * PV + q) * 4 + 3]);
-                    fix |= li[part] == kLidxGlobal;
+                    fix |= sl == kLidxGlobal;
                 }
                 return fix;
             };
@@ -326,7 +342,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
             };
             unsigned long long cm = kb_mask_from(om);
             const int nact = __popcll(cm);
+#ifdef TODA_TS_TIMELINE
             if (dbg && blockIdx.x == 0 && tid == 256 && it < 256) dbg[10 * 256 + it] = gbase;
+#endif
             int j = 0;
             while (cm) {
                 const int kbA = __ffsll((long long)cm) - 1;
@@ -338,8 +356,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
                 }
                 const int gA = gbase + j;
                 const int pj = j >> 1;
+                const int gp = gpbase + pj;             // global pair index: A slot gp % kASlots (two 32-column blocks)
+                const int aslot = gp % kASlots;
                 j += 2;
-                if ((pj & 1) != wg) continue;
+                if ((gp & 3) != wg) continue;
                 TS_DBG((tid & 127) == 0, 0, gA);
                 const int k_first = CIN == 128 ? (kbA >> 1) : kbA * PARTS;
                 release_below((int)(k_first >= gs) + (int)(k_first >= gs2));    // slabs of earlier groups are no longer read by this warp
@@ -349,45 +369,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
                     const int k_last = min(CIN == 128 ? (kb_last >> 1) : kb_last * PARTS + PARTS - 1, kvol - 1);
                     wait_group((int)(k_last >= gs) + (int)(k_last >= gs2));
                 }
-                uint32_t va[32], vb[32];
-                bool fix = false;
-                if (!(xmode & 1)) {
-                    fix = load_block(kbA, va);
-                    if (kbB >= 0) fix |= load_block(kbB, vb);
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) va[q] = vb[q] = 0u;
-                }
-                // the A slots are waited for only now: the barrier probe overlaps the shared-memory loads in flight.
-                // The MMAs retire in order: once the later slot of the pair is free, so is the earlier one.
-                const int g_last = kbB >= 0 ? gA + 1 : gA;
-                if (g_last >= kASlots) {
-                    mbar_wait(a_empty + 8 * (g_last & (kASlots - 1)), ((g_last >> 3) - 1) & 1);
+                // the two K blocks of the pair go through the same 32 registers one after the other (the A slot is waited
+                // for only after the first block's loads are in flight: the barrier probe overlaps them)
+                uint32_t va[32];
+                bool fix = load_block(kbA, va);
+                if (gp >= kASlots) {
+                    mbar_wait(a_empty + 8 * aslot, ((gp / kASlots) - 1) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 TS_DBG((tid & 127) == 0, 12, gA);
-                if (__any_sync(0xffffffffu, fix)) {
-                    fix_block(kbA, va);
-                    if (kbB >= 0) fix_block(kbB, vb);
-                }
+                if (__any_sync(0xffffffffu, fix)) fix_block(kbA, va);
                 __syncwarp();
-                TS_DBG((tid & 127) == 0, 2, gA);
-                if (!(xmode & 2)) {
-                    TS_STTM_X32(t_lane + (gA & (kASlots - 1)) * 32, va);
-                    if (kbB >= 0) TS_STTM_X32(t_lane + ((gA + 1) & (kASlots - 1)) * 32, vb);
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                } else if (va[0] == 0x12345u && vb[3] == 0x777u) {
-                    y[0] = 1.f;      // keep the loads alive
+                TS_STTM_X32(t_lane + aslot * 64, va);
+                if (kbB >= 0) {
+                    fix = load_block(kbB, va);
+                    if (__any_sync(0xffffffffu, fix)) fix_block(kbB, va);
+                    __syncwarp();
+                    TS_STTM_X32(t_lane + aslot * 64 + 32, va);
                 }
+                TS_DBG((tid & 127) == 0, 2, gA);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(a_full + 8 * (gA & (kASlots - 1)));
-                    if (kbB >= 0) mbar_arrive(a_full + 8 * ((gA + 1) & (kASlots - 1)));
-                }
+                if (lane == 0) mbar_arrive(a_full + 8 * aslot);
                 TS_DBG((tid & 127) == 0, 3, gA);
+                TS_DBG(lane == 0, 16 + (warp - kWarpGather0), gA);
             }
             gbase += nact;
+            gpbase += (nact + 1) >> 1;
             release_below(ngroups);
             __syncwarp();
             if (lane == 0 && !(xmode & 64)) mbar_arrive(lidx_empty + 8 * ib);
@@ -457,115 +466,83 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
             }
         }
     } else if (warp == kWarpMma) {
-        // ------------------------------------------------------------------ MMA issuer, software-pipelined inside the warp:
-        // while lane 0 issues the MMAs of pair p, lanes 1-3 already wait on the barriers of pair p+1 (a try_wait costs
-        // ~100 cycles even when the phase is long complete, the issue of 8 MMAs + commits ~300: serialised, the single
-        // issuing thread was the bottleneck of the small-N layers).  All lanes walk the same pair sequence.
+        // ------------------------------------------------------------------ MMA issuer.  The single issuing thread is the serial
+        // resource of the kernel (a tcgen05.mma costs ~45 cycles of issue whatever its N: scripts/ubench/commit_lat.cu), so the
+        // loop around it is kept minimal: ONE full-barrier per pair of K blocks, warp-uniform waits, 8 MMAs + 1-2 commits.
         constexpr uint32_t idesc = make_idesc_bf16(kTileM, COUT);
         if (BRES) mbar_wait(b_full, 0);
-        struct Pair { int valid, gA, n, kbA, kbB, first, last, it; };
-        int g_t = blockIdx.x - (int)gridDim.x, g_it = -1, g_j = 0, g_gbase = 0, g_nact = 0;
-        unsigned long long g_cm = 0ull;
-        uint32_t g_om_next = load_om(blockIdx.x);
-        auto next_pair = [&]() -> Pair {
-            Pair P;
-            P.valid = 0; P.gA = 0; P.n = 0; P.kbA = 0; P.kbB = -1; P.first = 0; P.last = 0; P.it = 0;
-            int first = 0;
-            if (!g_cm) {
-                g_t += gridDim.x;
-                ++g_it;
-                if (g_t >= num_tiles) return P;
-                g_gbase += g_nact;
-                const uint32_t om = g_om_next;
-                g_om_next = load_om(g_t + gridDim.x);
-                g_cm = kb_mask_from(om);
-                g_nact = __popcll(g_cm);
-                g_j = 0;
-                first = 1;
-            }
-            P.valid = 1;
-            P.kbA = __ffsll((long long)g_cm) - 1;
-            g_cm &= g_cm - 1;
-            if (g_cm) {
-                P.kbB = __ffsll((long long)g_cm) - 1;
-                g_cm &= g_cm - 1;
-            }
-            P.n = P.kbB >= 0 ? 2 : 1;
-            P.gA = g_gbase + g_j;
-            g_j += 2;
-            P.first = first;
-            P.last = g_cm == 0ull;
-            P.it = g_it;
-            return P;
-        };
-        auto wait_pair = [&](const Pair &P) {      // lanes 1..3 (and 4 for the second weight stage), each on its own barrier
-            if (!P.valid) return;
-            if (lane == 1) {
-                if (P.first && (P.it >> 1) > 0) mbar_wait(acc_empty + 8 * (P.it & 1), ((P.it >> 1) - 1) & 1);   // epilogue has drained this accumulator
-                mbar_wait(a_full + 8 * (P.gA & (kASlots - 1)), (P.gA >> 3) & 1);
-            } else if (lane == 2) {
-                if (P.n == 2) mbar_wait(a_full + 8 * ((P.gA + 1) & (kASlots - 1)), ((P.gA + 1) >> 3) & 1);
-            } else if (!BRES && lane == 3) {
-                mbar_wait(b_full + 8 * (P.gA % SB), (P.gA / SB) & 1);
-            } else if (!BRES && lane == 4) {
-                if (P.n == 2) mbar_wait(b_full + 8 * ((P.gA + 1) % SB), ((P.gA + 1) / SB) & 1);
-            }
-        };
-        Pair cur = next_pair();
-        wait_pair(cur);
-        Pair nxt = next_pair();
-        uint32_t accumulate = 0;
-        while (cur.valid) {
-            __syncwarp();                                   // the barriers of `cur` have been observed by lanes 1-4
-            if (elect_one()) {                              // (= lane 0; ELECT keeps the descriptors in uniform registers)
-                TS_DBG(true, 4, cur.gA);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d_tmem = tmem_base + (cur.it & 1) * COUT;
-                if (cur.first) accumulate = 0;
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    if (i < cur.n) {
-                        const int g = cur.gA + i, kb = i ? cur.kbB : cur.kbA;
-                        const int slot = g & (kASlots - 1), stage = BRES ? kb : g % SB;
-                        const uint64_t bd0 = make_desc_k_sw128(base + stage * C::kBStage);
-                        const uint32_t a0 = tmem_base + kACol0 + slot * 32;
-                        if (!(xmode & 4)) {
-                            umma_bf16_ts(d_tmem, a0, bd0, idesc, accumulate);
-#pragma unroll
-                            for (int jj = 1; jj < 4; ++jj) umma_bf16_ts(d_tmem, a0 + 8 * jj, bd0 + 2 * jj, idesc, 1u);   // K = 16: 8 columns / 32 bytes
-                        }
-                        accumulate = 1u;
-                        umma_commit(a_empty + 8 * slot);
-                        if (!BRES) umma_commit(b_empty + 8 * stage);
-                    }
+        int gbase = 0, gp = 0, it = 0;
+        uint32_t om_next = load_om(blockIdx.x);
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const int ab = it & 1, ause = it >> 1;
+            const uint32_t om = om_next;
+            om_next = load_om(t + gridDim.x);
+            TS_DBG(lane == 0, 14, it);
+            if (ause > 0) mbar_wait(acc_empty + 8 * ab, (ause - 1) & 1);   // epilogue has drained this accumulator
+            TS_DBG(lane == 0, 15, it);
+            const uint32_t d_tmem = tmem_base + ab * COUT;
+            uint32_t accumulate = 0;
+            unsigned long long cm = kb_mask_from(om);
+            const int nact = __popcll(cm);
+            int j = 0;
+            while (cm) {
+                const int kbA = __ffsll((long long)cm) - 1;
+                cm &= cm - 1;
+                int kbB = -1;
+                if (cm) {
+                    kbB = __ffsll((long long)cm) - 1;
+                    cm &= cm - 1;
                 }
-                if (cur.last) umma_commit(acc_full + 8 * (cur.it & 1));
-                TS_DBG(true, 5, cur.gA);
-            } else {
-                wait_pair(nxt);
+                const int gA = gbase + j;
+                const int n = kbB >= 0 ? 2 : 1;
+                j += 2;
+                const int aslot = gp % kASlots;
+                mbar_wait(a_full + 8 * aslot, (gp / kASlots) & 1);
+                if (!BRES) {
+                    mbar_wait(b_full + 8 * (gA % SB), (gA / SB) & 1);
+                    if (n == 2) mbar_wait(b_full + 8 * ((gA + 1) % SB), ((gA + 1) / SB) & 1);
+                }
+                TS_DBG(lane == 0, 4, gA);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        if (i < n) {
+                            const int g = gA + i, kb = i ? kbB : kbA;
+                            const int stage = BRES ? kb : g % SB;
+                            const uint64_t bd0 = make_desc_k_sw128(base + stage * C::kBStage);
+                            const uint32_t a0 = tmem_base + kACol0 + aslot * 64 + i * 32;
+                            if (!(xmode & 4)) {
+                                umma_bf16_ts(d_tmem, a0, bd0, idesc, accumulate);
+#pragma unroll
+                                for (int jj = 1; jj < 4; ++jj) umma_bf16_ts(d_tmem, a0 + 8 * jj, bd0 + 2 * jj, idesc, 1u);   // K = 16: 8 columns / 32 bytes
+                            }
+                            accumulate = 1u;
+                            if (!BRES) umma_commit(b_empty + 8 * stage);
+                        }
+                    }
+                    umma_commit(a_empty + 8 * aslot);
+                }
+                accumulate = 1u;
+                __syncwarp();
+                TS_DBG(lane == 0, 5, gA);
+                ++gp;
             }
-            cur = nxt;
-            nxt = next_pair();
+            gbase += nact;
+            if (elect_one()) umma_commit(acc_full + 8 * ab);
+            __syncwarp();
         }
-        __syncwarp();
     } else if (warp == kWarpLoader || warp == kWarpLoader2) {
-        // ------------------------------------------------------------------ loaders: table slice + row slabs, up to NB groups ahead.
-        // The two warps take alternate batches of 32 rows; a lane copies whole rows (ascending row ids: neighbouring lanes
-        // read neighbouring rows).
-        constexpr int P = C::kRowBytes / 16;               // 16-byte pieces per row
+        // ------------------------------------------------------------------ loaders (two warps: even / odd blocks; issuing a TMA costs
+        // ~65 cycles): table slice + row slabs, up to NB groups ahead.
+        // One TMA box copy (16 rows, hardware-swizzled) per cached block, lane i issuing block i of the unit.  The block list of
+        // unit u+1 is fetched while unit u is issued (a list read is two dependent L2 round trips).
         const int L = warp == kWarpLoader ? 0 : 1;
-        constexpr int NBAT = kMaxBatches / 2;
-        // the row list of unit u+1 is fetched while the copies of unit u are issued (a list read is two dependent L2 round trips)
-        int ids_n[NBAT], R_n = 0;
+        int bid_n = -1, nb_n = 0;
         auto fetch_unit = [&](int t, int grp) {
             if (t < num_tiles) {
-                R_n = __ldg(pcnt + (size_t)t * ngroups + grp);
-                const int *rows = prow + ((size_t)t * ngroups + grp) * cap;
-#pragma unroll
-                for (int i = 0; i < NBAT; ++i) {
-                    const int r = (2 * i + L) * 32 + lane;
-                    ids_n[i] = r < R_n ? __ldg(rows + r) : -1;
-                }
+                nb_n = __ldg(pcnt + (size_t)t * ngroups + grp);
+                bid_n = lane < nb_n ? __ldg(prow + ((size_t)t * ngroups + grp) * cap + lane) : -1;
             }
         };
         fetch_unit(blockIdx.x, 0);
@@ -582,30 +559,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
             for (int grp = 0; grp < ngroups && !(xmode & 32); ++grp) {
                 const int u = it * ngroups + grp, buf = u % NB, use = u / NB;
                 TS_DBG(L == 0 && lane == 0, 7, u);
-                int ids[NBAT];
-#pragma unroll
-                for (int i = 0; i < NBAT; ++i) ids[i] = ids_n[i];
-                const int R = R_n;
+                const int bid = bid_n, nb = nb_n;
                 if (grp + 1 < ngroups) fetch_unit(t, grp + 1);
                 else fetch_unit(t + gridDim.x, 0);
                 if (use > 0) mbar_wait(slab_empty + 8 * buf, (use - 1) & 1);
-                if (dbg && blockIdx.x == 0 && L == 0 && lane == 0 && u < 256) dbg[11 * 256 + u] = R;
                 TS_DBG(L == 0 && lane == 0, 8, u);
-                const uint32_t dst0 = slab_base + buf * C::kSlab + lane * C::kStride;
-#pragma unroll
-                for (int i = 0; i < NBAT; ++i) {
-                    if (ids[i] >= 0 && !(xmode & 8)) {
-                        const char *src = (const char *)xb + (size_t)ids[i] * C::kRowBytes;
-                        const uint32_t dst = dst0 + (2 * i + L) * 32 * C::kStride;
-#pragma unroll
-                        for (int jj = 0; jj < P; ++jj) cp_async_16(dst + 16 * jj, src + 16 * jj);
-                    }
+                if (L == 0 && lane == 0) {
+                    if (nb > 0 && !(xmode & 8)) mbar_arrive_expect_tx(slab_full + 8 * buf, (uint32_t)nb * 16u * C::kRowBytes);
+                    else mbar_arrive(slab_full + 8 * buf);
                 }
-                cp_async_arrive_noinc(slab_full + 8 * buf);
+                __syncwarp();
+                if (bid >= 0 && (lane & 1) == L && !(xmode & 8)) {
+                    const uint32_t dst = slab_base + buf * C::kSlab + lane * (16 * C::kRB);
+#pragma unroll
+                    for (int h = 0; h < C::kHalves; ++h)
+                        tma_load_2d(dst + h * C::kHalfSlab, &map_x, h * 64, bid * 16, slab_full + 8 * buf);
+                }
                 TS_DBG(L == 0 && lane == 0, 9, u);
             }
         }
-        asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
         // ------------------------------------------------------------------ weight producer
         if (lane == 0) {
@@ -636,10 +608,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Plan: one CTA (128 threads = the tile's rows) per (tile, offset group).  The distinct neighbour rows of the group are
-// found with a shared-memory bitmap over the window [min row, min row + 32768): set bits, prefix popcount = slot of
-// every row in ascending row order (sorted lists keep the slab fill coalesced).  Rows outside the window or beyond the
-// slab capacity are flagged kLidxGlobal and read from global memory by the conv kernel.  Deterministic.
+// Plan: one CTA (128 threads = the tile's rows) per (tile, offset group).  The cache unit is a BLOCK of 16 consecutive rows
+// of x (one TMA box).  The distinct blocks the group touches are found with a shared-memory bitmap over the window
+// [min block, min block + 32768): set bits, prefix popcount = slot of every block in ascending order; a table entry
+// becomes 16 * block slot + (row & 15).  Rows outside the window or beyond the slab capacity are flagged kLidxGlobal and
+// read from global memory by the conv kernel.  Deterministic.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kPlanWords = kPlanWindow / 32;       // 1024
 __global__ void __launch_bounds__(128) tile_plan_kernel(const int *__restrict__ nbr, int n_out, int kvol, int ngroups, int cap,
@@ -658,7 +631,7 @@ __global__ void __launch_bounds__(128) tile_plan_kernel(const int *__restrict__ 
     for (int j = 0; j < 9; ++j) {
         v[j] = -1;
         if (j < gs && row < n_out) v[j] = __ldg(nbr + (size_t)(grp * gs + j) * n_out + row);
-        if (v[j] >= 0) mn = min(mn, v[j]);
+        if (v[j] >= 0) mn = min(mn, v[j] >> 4);
     }
     for (int w = tid; w < kPlanWords; w += 128) bits[w] = 0u;
     for (int o = 16; o; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
@@ -668,7 +641,7 @@ __global__ void __launch_bounds__(128) tile_plan_kernel(const int *__restrict__ 
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
         if (v[j] >= 0) {
-            const unsigned d = (unsigned)(v[j] - base);
+            const unsigned d = (unsigned)((v[j] >> 4) - base);
             if (d < (unsigned)kPlanWindow) atomicOr(&bits[d >> 5], 1u << (d & 31));
         }
     }
@@ -714,11 +687,11 @@ __global__ void __launch_bounds__(128) tile_plan_kernel(const int *__restrict__ 
         if (j < gs) {
             uint32_t li = kLidxNone;
             if (v[j] >= 0) {
-                const unsigned d = (unsigned)(v[j] - base);
+                const unsigned d = (unsigned)((v[j] >> 4) - base);
                 li = kLidxGlobal;
                 if (d < (unsigned)kPlanWindow) {
                     const int slot = (int)pref[d >> 5] + __popc(bits[d >> 5] & ((1u << (d & 31)) - 1u));
-                    if (slot < cap) li = (uint32_t)slot;
+                    if (slot < cap) li = (uint32_t)(slot * 16 + (v[j] & 15));
                 }
             }
             lt[(size_t)j * kTileM] = (uint16_t)li;
@@ -727,7 +700,7 @@ __global__ void __launch_bounds__(128) tile_plan_kernel(const int *__restrict__ 
 }
 
 template <int CIN, int COUT>
-int launch_ts(const __nv_bfloat16 *xb, const int32_t *nbr, int n_out, int kvol, const TilePlan &plan, const __nv_bfloat16 *wb,
+int launch_ts(const __nv_bfloat16 *xb, int n_in, const int32_t *nbr, int n_out, int kvol, const TilePlan &plan, const __nv_bfloat16 *wb,
               const float *bias, const float *addend, float *y, const int32_t *out_rows, const uint32_t *tile_masks, double *bn_sums,
               cudaStream_t st) {
     using C = TsCfg<CIN, COUT>;
@@ -735,8 +708,9 @@ int launch_ts(const __nv_bfloat16 *xb, const int32_t *nbr, int n_out, int kvol, 
         toda_set_error("conv_ts_fwd: plan capacity %d exceeds the slab capacity %d of Cin=%d", plan.cap, C::kCap, CIN);
         return TODA_ERR_INVALID;
     }
-    CUtensorMap map_w;
+    CUtensorMap map_w, map_x;
     if (int rc = conv_tma_make_map(&map_w, wb, (uint64_t)COUT, (uint64_t)kvol * CIN, (uint32_t)COUT, 64)) return rc;
+    if (int rc = conv_tma_make_map(&map_x, xb, (uint64_t)n_in, (uint64_t)CIN, 16u, (uint32_t)(CIN < 64 ? CIN : 64))) return rc;
     const int num_tiles = ceil_div(n_out, kTileM);
     const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
     static bool attr_set = false;      // per <CIN, COUT> instantiation
@@ -745,7 +719,7 @@ int launch_ts(const __nv_bfloat16 *xb, const int32_t *nbr, int n_out, int kvol, 
         attr_set = true;
     }
     conv_ts_fwd_kernel<CIN, COUT><<<grid, kThreads, C::kSmem, st>>>(xb, nbr, n_out, kvol, plan.lidx, plan.rows, plan.cnt, plan.ngroups,
-                                                                   plan.cap, map_w, bias, addend, y, out_rows, tile_masks, bn_sums,
+                                                                   plan.cap, map_x, map_w, bias, addend, y, out_rows, tile_masks, bn_sums,
                                                                    num_tiles, conv_tc_debug_timeline(), conv_tc_debug_mode());
     TODA_LAUNCH_OK();
     return TODA_OK;
@@ -776,14 +750,13 @@ bool conv_ts_supported(int cin, int cout, int kvol, const TilePlan *plan) {
 int conv_ts_fwd(const void *xb, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const TilePlan &plan, const void *wb,
                 int cout, const float *bias, const float *addend, float *y, const int32_t *out_rows, const uint32_t *tile_masks,
                 double *bn_sums, cudaStream_t st) {
-    (void)n_in;
     const __nv_bfloat16 *x = (const __nv_bfloat16 *)xb, *w = (const __nv_bfloat16 *)wb;
 #define CASE_CO(CI)                                                                                                          \
     switch (cout) {                                                                                                          \
-        case 16: return launch_ts<CI, 16>(x, nbr, n_out, kvol, plan, w, bias, addend, y, out_rows, tile_masks, bn_sums, st);   \
-        case 32: return launch_ts<CI, 32>(x, nbr, n_out, kvol, plan, w, bias, addend, y, out_rows, tile_masks, bn_sums, st);   \
-        case 64: return launch_ts<CI, 64>(x, nbr, n_out, kvol, plan, w, bias, addend, y, out_rows, tile_masks, bn_sums, st);   \
-        case 128: return launch_ts<CI, 128>(x, nbr, n_out, kvol, plan, w, bias, addend, y, out_rows, tile_masks, bn_sums, st); \
+        case 16: return launch_ts<CI, 16>(x, n_in, nbr, n_out, kvol, plan, w, bias, addend, y, out_rows, tile_masks, bn_sums, st);   \
+        case 32: return launch_ts<CI, 32>(x, n_in, nbr, n_out, kvol, plan, w, bias, addend, y, out_rows, tile_masks, bn_sums, st);   \
+        case 64: return launch_ts<CI, 64>(x, n_in, nbr, n_out, kvol, plan, w, bias, addend, y, out_rows, tile_masks, bn_sums, st);   \
+        case 128: return launch_ts<CI, 128>(x, n_in, nbr, n_out, kvol, plan, w, bias, addend, y, out_rows, tile_masks, bn_sums, st); \
     }                                                                                                                        \
     break;
     switch (cin) {
@@ -803,7 +776,7 @@ extern "C" int toda_table_tile_plan(const int32_t *nbr, int n_out, int kvol, int
                                     int32_t *cnt, void *stream) {
     TODA_CHECK_ARG(n_out >= 0 && kvol > 0 && kvol <= kMaxKvol, "table_tile_plan: bad sizes n_out=%d kvol=%d", n_out, kvol);
     TODA_CHECK_ARG(ngroups >= 1 && ngroups <= 3 && kvol % ngroups == 0 && kvol / ngroups <= 9, "table_tile_plan: bad groups %d", ngroups);
-    TODA_CHECK_ARG(cap >= 1 && cap <= 32 * kMaxBatches, "table_tile_plan: bad capacity %d", cap);
+    TODA_CHECK_ARG(cap >= 1 && cap <= 32, "table_tile_plan: bad capacity %d", cap);
     if (n_out == 0) return TODA_OK;
     TODA_CHECK_ARG(nbr && lidx && rows && cnt, "table_tile_plan: null pointer");
     const int num_tiles = ceil_div(n_out, kTileM);

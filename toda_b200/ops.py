@@ -474,9 +474,20 @@ def rulebook_sparse(index_in: OccupancyIndex, ksize, stride, padding, tag, cin=N
     return rb, index_out
 
 
-# TODA_TILE_PLANS=0 keeps the round-1 tensor-core kernels (no row cache) for A/B measurements
+# Row-cache plans (toda_table_tile_plan) + the TMEM-operand kernel of conv_ts.cu.  Off by default: on the bench batch the
+# kernel is ~7 % faster than the cp.async / gather4 kernels over forward + dgrad, but building nine plans per batch costs the
+# (host-bound) step more than that (profiles/r02_conv_ts.md).  TODA_TILE_PLANS=1 or set_tile_plans(True) enables it.
 import os as _os
-_TILE_PLANS = _os.environ.get("TODA_TILE_PLANS", "1") != "0"
+_TILE_PLANS = _os.environ.get("TODA_TILE_PLANS", "0") != "0"
+
+
+def set_tile_plans(on):
+    global _TILE_PLANS
+    _TILE_PLANS = bool(on)
+
+
+def tile_plans_enabled():
+    return _TILE_PLANS
 
 
 def table_tile_masks(nbr):
