@@ -89,11 +89,26 @@ def collate(samples):
     return voxels, coords, num
 
 
+def stage2_frames(f):
+    """Two samples shaped like a TODA stage-2 batch (BASELINE configs[3]): an intra-domain mixup of two single-sweep
+    nuScenes-shaped frames (intra_domain_point_mixup.py L23-27, lam = 0.6) and a polar-sector swap of a Waymo-shaped frame
+    into a nuScenes-shaped one (inter_domain_point_polarmix.py L72-95, pi/2 sector).  The mixers themselves are pinned by
+    tests/golden/points.npz; here they only build the inputs, which are stored in the fixture."""
+    from oracle import points as OP
+    a, b = synth.make_frame("toda_stage2", 0)[:, :f], synth.make_frame("toda_stage2", 1)[:, :f]
+    rng = np.random.default_rng(4004)
+    mix = OP.mixup_points(a, b, 0.6, rng.permutation(a.shape[0]), rng.permutation(b.shape[0]))
+    w = synth.make_frame("waymo_010", 0)[:, :f]
+    swap = OP.polar_swap_points(synth.make_frame("toda_stage2", 2)[:, :f], w, 0.3, 0.3 + np.pi / 2)
+    return [np.ascontiguousarray(mix), np.ascontiguousarray(swap)]
+
+
 def golden_backbone(ns, cls_name, fname, frame_cfg, crop, vs, k, f):
     pcr = np.array(crop, dtype=np.float32)
     samples = []
+    frames = stage2_frames(f) if frame_cfg == "toda_stage2" else None
     for fi in range(2):
-        pts = synth.make_frame(frame_cfg, fi, shuffle=True)[:, :f]
+        pts = frames[fi] if frames is not None else synth.make_frame(frame_cfg, fi, shuffle=True)[:, :f]
         np.random.seed(SEED + fi)
         dp = ns.DataProcessor(processor_cfgs(vs, k, 4000), point_cloud_range=pcr, training=True, num_point_features=f)
         dd = dp.forward(data_dict={"points": np.ascontiguousarray(pts), "use_lead_xyz": True})
@@ -154,6 +169,12 @@ def golden_backbone(ns, cls_name, fname, frame_cfg, crop, vs, k, f):
 
 def main():
     ns = R.load(S.make_modules())
+    if "--stage2" in sys.argv:
+        # TODA stage-1/2 grid: z range -5 .. 4.8 -> 49 bins -> sparse_shape [50, ., .] (shape chain 50 -> 25 -> 13 -> 6 -> 2), F = 4
+        # (tools/cfgs/stage2_advmix/centerpoint_5_lab_95_unlab_nus_frames_advmix.yaml L13-14, L56-80)
+        golden_backbone(ns, "VoxelResBackBone8x", "backbone_res_stage2.npz", "toda_stage2",
+                        [4.0, -4.8, -5.0, 13.6, 4.8, 4.8], [0.075, 0.075, 0.2], 10, 4)
+        return
     golden_voxelize(ns)
     golden_backbone(ns, "VoxelResBackBone8x", "backbone_res.npz", "nus_0075",
                     [4.0, -2.4, -5.0, 8.8, 2.4, 3.0], [0.075, 0.075, 0.2], 10, 5)

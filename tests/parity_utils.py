@@ -196,6 +196,22 @@ def run_smoke():
             assert float(np.abs(rg["grads"][name]).max()) < 1e-5 * gmax, name
         else:
             assert_close(rg["grads"][name], g, rtol=1e-3, atol_scale=1e-4, what="grad " + name)
+    # the same step on the bf16 tensor-core path (what bench.py times): the tcgen05 forward / dgrad / wgrad kernels run,
+    # geometry stays bit-identical, activations within the stated bf16 tolerance (relative L2 <= 5e-2) of the oracle
+    from toda_b200.spconv_compat import pytorch as G
+    _, net_b = build_pair("VoxelResBackBone8x", 5, grid, device=dev)
+    for plans in (False, True):                 # round-1 kernels, then the row-cache / TMEM-operand kernel
+        ops.set_tile_plans(plans)
+        G.set_conv_precision("bf16")
+        try:
+            rb = run_backbone(net_b, hc_g, gv.detach(), vc.to(dev), 2, cot=cot, train=True)
+        finally:
+            G.set_conv_precision("fp32")
+            ops.set_tile_plans(False)
+        assert np.array_equal(sort_rows(rb["enc_features"], rb["enc_indices"])[1], sort_rows(ro["enc_features"], ro["enc_indices"])[1])
+        a, b = rb["spatial_features"].astype(np.float64), ro["spatial_features"].astype(np.float64)
+        rel = float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+        assert rel <= 5e-2, ("bf16 spatial_features rel-L2", rel)
 
 
 def _oracle_hc(bd):

@@ -269,12 +269,18 @@ def test_bev_scatter_bit_exact_and_backward():
 
 
 # ------------------------------------------------------------------------------------------ end to end
-@pytest.mark.parametrize("cls,fname", [("VoxelResBackBone8x", "backbone_res.npz"), ("VoxelBackBone8x", "backbone_voxel.npz")])
+@pytest.mark.parametrize("cls,fname", [("VoxelResBackBone8x", "backbone_res.npz"), ("VoxelBackBone8x", "backbone_voxel.npz"),
+                                       ("VoxelResBackBone8x", "backbone_res_stage2.npz")])
 def test_backbone_vs_reference_golden(cls, fname):
-    """Golden vectors produced through the reference's own spconv_backbone.py + height_compression.py."""
+    """Golden vectors produced through the reference's own spconv_backbone.py + height_compression.py.
+    backbone_res_stage2: the TODA stage-2 geometry (z range -5..4.8 -> sparse_shape [50, ., .], F = 4, mixup / polar-swap
+    samples; BASELINE configs[3])."""
     import toda_b200.pcdet_plugin as P
     g = PU.load_golden(fname)
-    twin, net = PU.build_pair(cls, 5, g["grid_size"], seed=int(g["seed"]))
+    nf = int(g["voxel_features"].shape[1])
+    if "stage2" in fname:
+        assert int(g["grid_size"][2]) == 49
+    twin, net = PU.build_pair(cls, nf, g["grid_size"], seed=int(g["seed"]))
     hc = P.HeightCompression(PU.Cfg(NUM_BEV_FEATURES=256))
     vf = torch.from_numpy(g["voxel_features"]).to(DEV)
     vc = torch.from_numpy(g["voxel_coords"]).float().to(DEV)       # float32 coords, as load_data_to_gpu delivers
@@ -284,14 +290,26 @@ def test_backbone_vs_reference_golden(cls, fname):
     assert np.array_equal(i_sorted, g["train_enc_indices"])
     PU.assert_close(f_sorted, g["train_enc_features"], what="encoded features")
     assert abs(r["loss"] - float(g["train_loss"])) < 1e-3 * max(1.0, abs(float(g["train_loss"])))
-    # d loss / d voxel_features comes back in the caller's (golden) row order
-    PU.assert_close(r["dvoxel_features"], g["train_dvoxel_features"], rtol=1e-3, what="d voxel_features")
     names = [str(n) for n in g["grad_names"]]
     norms = np.array([np.linalg.norm(r["grads"][n].astype(np.float64)) for n in names])
-    # conv biases feeding a BatchNorm have a mathematically zero gradient: their golden norms (~1e-3 next to
-    # ~1e4 for the weights) are rounding noise, hence the absolute floor
-    np.testing.assert_allclose(norms, g["grad_norms"], rtol=2e-3, atol=1e-6 * float(g["grad_norms"].max()))
-    PU.assert_close(r["grads"]["conv_input.0.weight"], g["grad_conv_input_weight"], rtol=1e-3, atol_scale=1e-4, what="wgrad in")
+    if "stage2" in fname:
+        # This crop holds ONE activation (x_conv4, 2.3e-6 in the fp32 reference, 0 here) that sits on the ReLU kink: its mask
+        # flips under fp32 accumulation-order noise and moves every gradient upstream of conv4 by ~0.5 % (verified element by
+        # element with scripts/debug_stage2_golden.py: d x_conv4 agrees to 2e-6, conv_out's gradients to 2e-6, 1 flipped mask
+        # of 120 320).  Gradients below the flip are therefore bounded in relative L2; everything else stays at rtol 1e-3.
+        def rl2(a, b):
+            a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+            return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+        assert rl2(r["dvoxel_features"], g["train_dvoxel_features"]) <= 2e-2
+        np.testing.assert_allclose(norms, g["grad_norms"], rtol=2e-2, atol=1e-6 * float(g["grad_norms"].max()))
+        assert rl2(r["grads"]["conv_input.0.weight"], g["grad_conv_input_weight"]) <= 2e-2
+    else:
+        # d loss / d voxel_features comes back in the caller's (golden) row order
+        PU.assert_close(r["dvoxel_features"], g["train_dvoxel_features"], rtol=1e-3, what="d voxel_features")
+        # conv biases feeding a BatchNorm have a mathematically zero gradient: their golden norms (~1e-3 next to
+        # ~1e4 for the weights) are rounding noise, hence the absolute floor
+        np.testing.assert_allclose(norms, g["grad_norms"], rtol=2e-3, atol=1e-6 * float(g["grad_norms"].max()))
+        PU.assert_close(r["grads"]["conv_input.0.weight"], g["grad_conv_input_weight"], rtol=1e-3, atol_scale=1e-4, what="wgrad in")
     PU.assert_close(r["grads"]["conv_out.0.weight"], g["grad_conv_out_weight"], rtol=1e-3, atol_scale=1e-4, what="wgrad out")
     PU.assert_close(net.conv_input[1].running_mean.cpu().numpy(), g["running_mean_conv_input"], what="running_mean")
     PU.assert_close(net.conv_input[1].running_var.cpu().numpy(), g["running_var_conv_input"], what="running_var")
@@ -301,7 +319,7 @@ def test_backbone_vs_reference_golden(cls, fname):
         assert np.array_equal(is_, gi)
         PU.assert_close(fs, gs, what=k)
     # eval mode (running statistics) from a fresh copy of the initial weights
-    twin2, net2 = PU.build_pair(cls, 5, g["grid_size"], seed=int(g["seed"]))
+    twin2, net2 = PU.build_pair(cls, nf, g["grid_size"], seed=int(g["seed"]))
     with torch.no_grad():
         r2 = PU.run_backbone(net2, hc, vf, vc, 2, train=False)
     f2, i2 = PU.sort_rows(r2["enc_features"], r2["enc_indices"])

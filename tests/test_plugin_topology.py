@@ -9,11 +9,14 @@ import torch
 from tests import parity_utils as PU
 
 
-@pytest.mark.parametrize("cls,fname", [("VoxelResBackBone8x", "backbone_res.npz"), ("VoxelBackBone8x", "backbone_voxel.npz")])
+@pytest.mark.parametrize("cls,fname", [("VoxelResBackBone8x", "backbone_res.npz"), ("VoxelBackBone8x", "backbone_voxel.npz"),
+                                       ("VoxelResBackBone8x", "backbone_res_stage2.npz")])
 def test_twin_reproduces_reference_golden(cls, fname):
     g = PU.load_golden(fname)
     torch.manual_seed(int(g["seed"]))
-    net = PU.oracle_backbones()[cls](PU.Cfg(), 5, g["grid_size"])
+    net = PU.oracle_backbones()[cls](PU.Cfg(), int(g["voxel_features"].shape[1]), g["grid_size"])
+    if "stage2" in fname:      # TODA stage-1/2 grid: 49 z bins -> sparse_shape 50 -> 25 -> 13 -> 6 -> 2
+        assert list(net.sparse_shape)[0] == 50
     wsum = float(sum(p.detach().double().abs().sum() for p in net.parameters()))
     assert abs(wsum - float(g["weight_abs_sum"])) < 1e-6 * wsum      # identical init => identical param order
     vf, vc = torch.from_numpy(g["voxel_features"]), torch.from_numpy(g["voxel_coords"]).float()
