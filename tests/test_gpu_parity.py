@@ -377,3 +377,31 @@ def test_parity_order_is_a_stable_class_sort(stride, padding, n):
         blk = t[:, tile * 128:(tile + 1) * 128]
         want_mask = sum((1 << k) for k in range(27) if (blk[k] >= 0).any())
         assert int(masks[tile]) == want_mask, tile
+
+
+def test_two_shape_preserving_sparse_convs_without_indice_key():
+    """SparseConv3d k3 s1 p1 keeps the spatial shape, and convs with indice_key=None share one tag: the output index must
+    not alias (and un-mark) the input index (rulebook_sparse aliasing)."""
+    from oracle import spconv_oracle as S
+    from toda_b200.spconv_compat import pytorch as G
+    torch.manual_seed(0)
+    shape, n, batch = [9, 20, 20], 800, 2
+
+    def build(sp):
+        return sp.SparseSequential(sp.SparseConv3d(8, 8, 3, stride=1, padding=1, bias=True), sp.SparseConv3d(8, 16, 3, stride=1, padding=1, bias=False),
+                                   sp.SparseConv3d(16, 8, 1, stride=1, padding=0, bias=False))
+    a, b = build(S), build(G)
+    b.load_state_dict(a.state_dict())
+    b = b.to(DEV)
+    feats, idx = PU.random_sparse(11, batch, shape, n, 8)
+    fa = torch.from_numpy(feats).requires_grad_(True)
+    fb = torch.from_numpy(feats).to(DEV).requires_grad_(True)
+    ya = a(S.SparseConvTensor(fa, torch.from_numpy(idx), shape, batch))
+    yb = b(G.SparseConvTensor(fb, torch.from_numpy(idx).to(DEV), shape, batch))
+    fa_s, ia = PU.sort_rows(ya.features.detach().numpy(), ya.indices.numpy())
+    fb_s, ib = PU.sort_rows(yb.features.detach().cpu().numpy(), yb.indices.cpu().numpy())
+    assert np.array_equal(ia, ib)
+    PU.assert_close(fb_s, fa_s, what="chained shape-preserving SparseConv3d")
+    ya.features.sum().backward()
+    yb.features.sum().backward()
+    PU.assert_close(fb.grad.cpu().numpy(), fa.grad.numpy(), rtol=1e-3, what="dgrad through the chain")

@@ -166,6 +166,57 @@ def test_bf16_vs_fp32_full_size_frame():
     assert c_dx >= 0.9 and min(c_w.values()) >= 0.9
 
 
+def test_bf16_gradients_with_frozen_masks_full_size_frame():
+    """The numeric gradient bound of the bf16 path: one full-size nuScenes-shaped frame, fp32 FFMA path vs bf16 tcgen05 path
+    with identical weights AND identical ReLU masks (recorded in the fp32 pass, imposed on the bf16 pass with
+    ops.ReluMaskTape), so that what is compared is the arithmetic (bf16-rounded operands, fp32 accumulation, 21 layers,
+    batch-statistics BatchNorm), not the mask flips a perturbed forward pass causes.  Stated tolerance: relative L2 of
+    d loss / d voxel_features and of every conv weight gradient <= 3e-2 (measured: see the printed line)."""
+    import toda_b200.pcdet_plugin as P
+    from toda_b200 import ops, synth
+    from toda_b200.spconv_compat import pytorch as G
+    cfg = synth.CONFIGS["nus_0075"]
+    frames, collated = synth.make_batch("nus_0075", 1)
+    grid = synth.grid_size_xyz(cfg["pc_range"], cfg["voxel_size"])
+    pts = torch.from_numpy(collated).to(DEV)
+    offs = torch.tensor([0, collated.shape[0]], dtype=torch.int32, device=DEV)
+    v, c, n, _ = ops.voxelize(pts, offs, cfg["pc_range"], cfg["voxel_size"], cfg["max_points"], cfg["max_voxels"]["train"],
+                              num_features=5, xyz_col=1, feat_col=1, order=ops.ORDER_CANONICAL)
+    vf = ops.mean_vfe(v, n)
+    hc = P.HeightCompression(PU.Cfg(NUM_BEV_FEATURES=256))
+    tape = ops.ReluMaskTape("record")
+    res = {}
+    try:
+        for mode in ("fp32", "bf16"):
+            torch.manual_seed(666)
+            net = P.VoxelResBackBone8x(PU.Cfg(), 5, grid).to(DEV).train()
+            G.set_conv_precision(mode)
+            ops.set_relu_mask_tape(tape)
+            x = vf.clone().requires_grad_(True)
+            bd = hc(net({"voxel_features": x, "voxel_coords": c, "batch_size": 1, "voxel_coords_canonical": True}))
+            sf = bd["spatial_features"]
+            cot = torch.randn(sf.shape, device=DEV, generator=torch.Generator(device=DEV).manual_seed(5))
+            (sf * cot).sum().backward()
+            res[mode] = dict(sf=sf.detach(), dx=x.grad, grads={k: p.grad.detach() for k, p in net.named_parameters()})
+            tape.replay()
+    finally:
+        ops.set_relu_mask_tape(None)
+        G.set_conv_precision("fp32")
+
+    def rl2(a, b):
+        return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+    e_sf = rl2(res["bf16"]["sf"], res["fp32"]["sf"])
+    e_dx = rl2(res["bf16"]["dx"], res["fp32"]["dx"])
+    e_w = {k: rl2(res["bf16"]["grads"][k], g) for k, g in res["fp32"]["grads"].items() if g.dim() == 5}
+    e_bn = {k: rl2(res["bf16"]["grads"][k], g) for k, g in res["fp32"]["grads"].items() if g.dim() == 1 and ".bn" in k or k.endswith(".1.weight") or k.endswith(".1.bias")}
+    print("bf16 vs fp32, masks frozen, full frame: spatial_features rel-L2 %.3e; d voxel_features %.3e; conv weight grads max %.3e "
+          "median %.3e; BN affine grads max %.3e" % (e_sf, e_dx, max(e_w.values()), float(np.median(list(e_w.values()))),
+                                                      max(e_bn.values())))
+    assert e_sf <= 3e-2 and e_dx <= 3e-2
+    assert max(e_w.values()) <= 3e-2, max(e_w.items(), key=lambda kv: kv[1])
+    assert max(e_bn.values()) <= 3e-2, max(e_bn.items(), key=lambda kv: kv[1])
+
+
 @pytest.mark.parametrize("cin,cout,n", [(16, 16, 300000), (32, 32, 200000), (64, 64, 150000), (128, 128, 60000), (64, 128, 90000)])
 def test_tc_matches_ffma_path_at_scale(cin, cout, n):
     """Many tiles per persistent CTA, ring / phase wrap-around, TMEM double buffering, split-K wgrad over thousands of

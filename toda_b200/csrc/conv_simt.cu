@@ -15,7 +15,7 @@ int conv_tc_wgrad(const float *x, const void *x_bf16, int n_in, int cin, const i
                   const float *dy, const void *dy_bf16, int cout, float *dw_param, void *workspace, size_t workspace_bytes,
                   cudaStream_t st);
 bool conv_tc_supported(int cin, int cout, int kvol);
-bool conv_tc_wgrad_supported(int cin, int cout);
+bool conv_tc_wgrad_supported(int cin, int cout, int kvol);
 size_t conv_tc_wgrad_workspace_bytes(int n_in, int n_out, int kvol, int cin, int cout);
 
 namespace {
@@ -319,7 +319,7 @@ static int spconv_fwd_impl(const float *x, const void *x_bf16, int n_in, int cin
 
 extern "C" size_t toda_spconv_wgrad_workspace_bytes(int n_in, int n_out, int kvol, int cin, int cout, int precision) {
     if (n_in < 0 || n_out < 0 || kvol <= 0 || cin <= 0 || cout <= 0) return 0;
-    if (precision == TODA_CONV_BF16 && conv_tc_wgrad_supported(cin, cout))
+    if (precision == TODA_CONV_BF16 && conv_tc_wgrad_supported(cin, cout, kvol))
         return conv_tc_wgrad_workspace_bytes(n_in, n_out, kvol, cin, cout);
     int splits = wgrad_splits(n_out, kvol, cin, cout);
     return align_up((size_t)splits * kvol * cin * cout * sizeof(float), 256);
@@ -337,7 +337,7 @@ extern "C" int toda_spconv_wgrad(const float *x, const void *x_bf16, int n_in, i
     }
     TODA_CHECK_ARG(x && nbr && dy && workspace, "spconv_wgrad: null pointer");
     TODA_CHECK_ARG(precision == TODA_CONV_FP32 || precision == TODA_CONV_BF16, "spconv_wgrad: unknown precision %d", precision);
-    if (precision == TODA_CONV_BF16 && conv_tc_wgrad_supported(cin, cout))
+    if (precision == TODA_CONV_BF16 && conv_tc_wgrad_supported(cin, cout, kvol))
         return conv_tc_wgrad(x, x_bf16, n_in, cin, nbr, n_out, kvol, dy, dy_bf16, cout, dw_param, workspace, workspace_bytes, st);
     int splits = wgrad_splits(n_out, kvol, cin, cout);
     size_t need = (size_t)splits * kvol * cin * cout * sizeof(float);

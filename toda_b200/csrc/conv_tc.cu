@@ -949,8 +949,9 @@ WgradPlan wgrad_plan(int n_in, int n_out, int kvol, int cin, int cout) {
 
 }  // namespace
 
-bool conv_tc_wgrad_supported(int cin, int cout) {
-    return ((cin >= 1 && cin <= 16) || cin == 32 || cin == 64 || cin == 128) && (cout == 16 || cout == 32 || cout == 64 || cout == 128);
+bool conv_tc_wgrad_supported(int cin, int cout, int kvol) {
+    // (the kernel's shared-memory table slice holds at most 32 offsets: larger kernels take the fp32 wgrad)
+    return kvol <= kMaxKvol && ((cin >= 1 && cin <= 16) || cin == 32 || cin == 64 || cin == 128) && (cout == 16 || cout == 32 || cout == 64 || cout == 128);
 }
 
 size_t conv_tc_wgrad_workspace_bytes(int n_in, int n_out, int kvol, int cin, int cout) {

@@ -106,8 +106,10 @@ _workspaces = {}
 
 
 def _workspace(tag, nbytes, device, zero=False):
-    """Grow-only cached scratch buffers (caller-owned memory in the ABI's terms)."""
-    key = (tag, device.index)
+    """Grow-only cached scratch buffers (caller-owned memory in the ABI's terms).  One buffer per (tag, device, STREAM):
+    the input pipeline runs the front of batch i+1 on a side stream while the main stream may still use the same tag, and
+    a block must never be shared (or regrown, which frees the old block into another stream's pool) across streams."""
+    key = (tag, device.index, torch.cuda.current_stream(device).cuda_stream)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = (torch.zeros if zero else torch.empty)(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
@@ -272,7 +274,7 @@ class OccupancyIndex:
         nbytes = _C.lib().toda_index_bytes(self.batch, d, h, w)
         if nbytes == 0:
             raise RuntimeError(f"bad index dims {batch} {shape}")
-        self.key = (("index", tag, self.batch, d, h, w), device.index)
+        self.key = (("index", tag, self.batch, d, h, w), device.index, torch.cuda.current_stream(device).cuda_stream)
         self.buf = _workspace(self.key[0], nbytes, device, zero=True)
         self.coords = None
         self.frame_counts = None
@@ -433,7 +435,7 @@ def rulebook_subm(index: OccupancyIndex, ksize, channels=None):
                   nbr, None)
     # even in raster order a 128-row tile often has no neighbour at all under whole groups of offsets (e.g. no dz = -1 /
     # +1 neighbours on flat ground): 45 % of the K chunks at stride 1, 15-20 % deeper; the kernel skips them
-    rb.tile_masks = table_tile_masks(nbr) if n > 0 else None
+    rb.tile_masks = table_tile_masks(nbr) if (n > 0 and kvol <= 32) else None
     rb.plan = table_tile_plan(nbr, ksize, channels) if _TILE_PLANS else None
     return rb
 
@@ -444,6 +446,11 @@ def rulebook_sparse(index_in: OccupancyIndex, ksize, stride, padding, tag, cin=N
     index_in.ensure_live()
     out_shape = [conv_out_size(index_in.shape[a], ksize[a], stride[a], padding[a]) for a in range(3)]
     index_out = OccupancyIndex(index_in.batch, out_shape, index_in.buf.device, tag)
+    if index_out.buf.data_ptr() == index_in.buf.data_ptr():
+        # same tag and same spatial shape as the input's index (e.g. two k3 s1 p1 SparseConv3d with indice_key=None in a row):
+        # acquiring the shared buffer would un-mark the input index and both tables would be built against one bitmap
+        index_out = OccupancyIndex(index_in.batch, out_shape, index_in.buf.device, (tag, "alt"))
+    assert index_out.buf.data_ptr() != index_in.buf.data_ptr()
     index_out.insert_strided(index_in.coords, ksize, stride, padding)
     per_in = 1
     for a in range(3):
@@ -464,8 +471,9 @@ def rulebook_sparse(index_in: OccupancyIndex, ksize, stride, padding, tag, cin=N
     _count(2)
     rb = Rulebook(False, list(ksize), list(stride), list(padding), index_in.shape, out_shape, n_in, n_out, out_coords,
                   nbr_fwd, nbr_bwd)
-    rb.tile_masks = table_tile_masks(nbr_fwd) if n_out > 0 else None
-    rb.dgrad_order, rb.nbr_bwd_sorted = _dgrad_parity_order(index_in.coords, nbr_bwd, stride, padding)
+    rb.tile_masks = table_tile_masks(nbr_fwd) if (n_out > 0 and kvol <= 32) else None
+    rb.dgrad_order, rb.nbr_bwd_sorted = (_dgrad_parity_order(index_in.coords, nbr_bwd, stride, padding) if kvol <= 32
+                                         else (None, None))
     if rb.dgrad_order is not None:
         rb.dgrad_tile_masks = table_tile_masks(rb.nbr_bwd_sorted)
     if _TILE_PLANS:
@@ -527,9 +535,16 @@ def _dgrad_parity_order(in_coords, nbr_bwd, stride, padding):
 _repack_cache = {}
 
 
+def invalidate_weight_cache():
+    """Drops the cached weight repacks.  The cache is validated by the parameter's autograd version counter, which
+    in-place writes through `.data` (pcdet's OptimWrapper true-weight-decay path `p.data.mul_()`, EMA / SWA swaps,
+    `.data.copy_()`) do NOT bump: call this after such an update (or after loading a checkpoint into live modules)."""
+    _repack_cache.clear()
+
+
 def _repack(weight, transpose, mirror):
     """[kvol][Cin][Cout] (or transposed / k-mirrored) copy of a (Cout,kz,ky,kx,Cin) parameter, cached until the
-    parameter is modified (optimizer step bumps ._version)."""
+    parameter is modified (optimizer step bumps ._version; for `.data` writes see invalidate_weight_cache)."""
     key = (id(weight), bool(transpose), bool(mirror))
     hit = _repack_cache.get(key)
     if hit is not None and hit[2]() is weight and hit[0] == weight._version and hit[3] == weight.data_ptr():
@@ -681,9 +696,32 @@ def col_sum(t):
 # ------------------------------------------------------------------------------------------------
 # K8 BatchNorm + ReLU (+ residual)
 # ------------------------------------------------------------------------------------------------
+class ReluMaskTape:
+    """Test instrument (tests/test_gpu_tc.py): records the ReLU masks of one pass ('record') and imposes them on another
+    ('replay'), so that two arithmetic modes can be compared with identical activation patterns -- the mask flips of a
+    perturbed forward pass otherwise dominate any end-to-end gradient comparison.  Not used on the product path."""
+
+    def __init__(self, mode):
+        assert mode in ("record", "replay")
+        self.mode, self.masks, self.i = mode, [], 0
+
+    def replay(self):
+        self.mode, self.i = "replay", 0
+        return self
+
+
+_relu_tape = None
+
+
+def set_relu_mask_tape(tape):
+    global _relu_tape
+    _relu_tape = tape
+
+
 def _bn_forward_impl(y, gamma, beta, running_mean, running_var, eps, momentum, training, residual, relu, want_bf16, sums,
                      need_grad):
-    """-> (a, a_bf16, y, mean, rstd)"""
+    """-> (a, a_bf16, y, mean, rstd, a_mask): a_mask is what the backward pass derives the ReLU mask from (`a` itself,
+    except under a ReluMaskTape)."""
     y = _need(y.contiguous(), torch.float32, "bn input")
     n, c = y.shape
     dev = y.device
@@ -715,11 +753,25 @@ def _bn_forward_impl(y, gamma, beta, running_mean, running_var, eps, momentum, t
     res = residual.contiguous() if residual is not None else None
     a = torch.empty_like(y)
     ab = torch.empty(y.shape, dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    if _relu_tape is not None and relu:
+        # pre-activation z, then the recorded / replayed mask (test instrument, see ReluMaskTape)
+        _C.check(L.toda_bn_apply(_p(y), n, c, _p(scale), _p(shift), _p(res), 0, _p(a), None, _stream()), "toda_bn_apply")
+        _count(1)
+        if _relu_tape.mode == "record":
+            mask = a > 0
+            _relu_tape.masks.append(mask)
+        else:
+            mask = _relu_tape.masks[_relu_tape.i]
+            _relu_tape.i += 1
+        a = a * mask
+        if want_bf16:
+            ab = a.to(torch.bfloat16)
+        return a, ab, y, mean, rstd, mask.to(torch.float32)
     with _timed("bn_apply", n=n, c=c, residual=res is not None):
         _C.check(L.toda_bn_apply(_p(y), n, c, _p(scale), _p(shift), _p(res), int(relu), _p(a), _p(ab), _stream()),
                  "toda_bn_apply")
     _count(1)
-    return a, ab, y, mean, rstd
+    return a, ab, y, mean, rstd, a
 
 
 def _bn_backward_impl(da, y, a, gamma, mean, rstd, training, relu, has_res, want_bf16):
@@ -744,9 +796,9 @@ def _bn_backward_impl(da, y, a, gamma, mean, rstd, training, relu, has_res, want
 class _BNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y, gamma, beta, running_mean, running_var, eps, momentum, training, residual, relu, want_bf16, sums):
-        a, ab, y, mean, rstd = _bn_forward_impl(y, gamma, beta, running_mean, running_var, eps, momentum, training, residual,
-                                                relu, want_bf16, sums, y.requires_grad or gamma.requires_grad)
-        ctx.save_for_backward(y, a, gamma, mean, rstd)
+        a, ab, y, mean, rstd, a_mask = _bn_forward_impl(y, gamma, beta, running_mean, running_var, eps, momentum, training,
+                                                        residual, relu, want_bf16, sums, y.requires_grad or gamma.requires_grad)
+        ctx.save_for_backward(y, a_mask, gamma, mean, rstd)
         ctx.set_materialize_grads(False)      # the bf16 copy is non-differentiable: no zero tensor for it in backward
         ctx.cfg = (bool(training), bool(relu), residual is not None, bool(want_bf16))
         if ab is not None:
@@ -773,9 +825,9 @@ class _ConvBNAct(torch.autograd.Function):
     def forward(ctx, x, x_bf16, weight, bias, rb, precision, gamma, beta, running_mean, running_var, eps, momentum, training,
                 residual, relu, want_bf16):
         y, sums, x, weight, x_bf16 = _conv_forward_impl(x, x_bf16, weight, bias, rb, precision, bool(training))
-        a, ab, y, mean, rstd = _bn_forward_impl(y, gamma, beta, running_mean, running_var, eps, momentum, training, residual,
-                                                relu, want_bf16, sums, True)
-        ctx.save_for_backward(x, weight, x_bf16, y, a, gamma, mean, rstd)
+        a, ab, y, mean, rstd, a_mask = _bn_forward_impl(y, gamma, beta, running_mean, running_var, eps, momentum, training,
+                                                        residual, relu, want_bf16, sums, True)
+        ctx.save_for_backward(x, weight, x_bf16, y, a_mask, gamma, mean, rstd)
         ctx.set_materialize_grads(False)
         ctx.rb, ctx.precision, ctx.has_bias = rb, precision, bias is not None
         ctx.cfg = (bool(training), bool(relu), residual is not None, bool(want_bf16))
