@@ -46,10 +46,24 @@ sys.path.insert(0, ROOT)
 
 from toda_b200 import synth  # noqa: E402
 
-WORKLOAD = "nus_0075"
 FRAMES_PER_GPU = 4
 POOL = 3                     # distinct pre-staged batches rotated through, so no step re-reads a warm input
-METRIC = "frames/s voxelize+VoxelResBackBone8x fwd+bwd"
+# The default line is BASELINE.json configs[2]; the other configs are measured with --workload and never replace it.
+WORKLOADS = {
+    "nus_0075": dict(cfg="nus_0075", net="VoxelResBackBone8x", train=True, metric="frames/s voxelize+VoxelResBackBone8x fwd+bwd",
+                     desc="BASELINE.json configs[2]: CenterPoint VoxelResBackBone8x fwd+bwd, nuScenes-shaped 10-sweep frames, 0.075 m "
+                          "voxels, grid 1440x1440x41, batch 4/GPU, train-mode BN, K=10, max_voxels 120000"),
+    "waymo_second": dict(cfg="waymo_010", net="VoxelBackBone8x", train=False, metric="frames/s voxelize+VoxelBackBone8x fwd",
+                         desc="BASELINE.json configs[1]: SECOND VoxelBackBone8x forward (eval-mode BN), Waymo-shaped frames, 0.1 m "
+                              "voxels, grid 1504x1504x41, batch 4/GPU, K=5, max_voxels 150000"),
+    "toda_stage2": dict(cfg="toda_stage2", net="VoxelResBackBone8x", train=True, mixed=True,
+                        metric="frames/s voxelize+VoxelResBackBone8x fwd+bwd (TODA stage-2 batch)",
+                        desc="BASELINE.json configs[3]: TODA stage-2 step, batch of 4 = 2 intra-domain mixups + 2 Waymo/nuScenes polar "
+                             "sector swaps (mixed on the host side of the timer), CenterPoint VoxelResBackBone8x fwd+bwd, grid "
+                             "1440x1440x50 (z -5..4.8), F=4, 1 sweep, K=10, max_voxels 120000"),
+}
+WORKLOAD = "nus_0075"
+METRIC = WORKLOADS[WORKLOAD]["metric"]
 
 
 class Cfg(dict):
@@ -144,26 +158,56 @@ def build_hot_path(device, precision):
     import toda_b200.pcdet_plugin as P
     from toda_b200.spconv_compat import pytorch as sp
     sp.set_conv_precision(precision)
-    cfg = synth.CONFIGS[WORKLOAD]
+    wl = WORKLOADS[WORKLOAD]
+    cfg = synth.CONFIGS[wl["cfg"]]
     grid = synth.grid_size_xyz(cfg["pc_range"], cfg["voxel_size"])
     torch.manual_seed(666)   # the reference's --fix_random_seed value
     vfe = P.MeanVFE(Cfg(MAX_POINTS_PER_VOXEL=cfg["max_points"], MAX_NUMBER_OF_VOXELS=cfg["max_voxels"]), cfg["num_features"],
                     voxel_size=cfg["voxel_size"], point_cloud_range=cfg["pc_range"], grid_size=grid)
-    net = P.VoxelResBackBone8x(Cfg(), cfg["num_features"], grid)
+    net = getattr(P, wl["net"])(Cfg(), cfg["num_features"], grid)
     hc = P.HeightCompression(Cfg(NUM_BEV_FEATURES=256))
     for m in (vfe, net, hc):
-        m.to(device).train()
+        m.to(device).train(wl["train"])
     return vfe, net, hc
 
 
-def host_batches(rank, n_batches):
-    """Pinned host copies of collated `points` [b,x,y,z,i,dt] (dataset.py L173-178) + frame offsets."""
+def _stage2_frames(first, device):
+    """Four stage-2 samples (BASELINE configs[3]): two intra-domain mixups (intra_domain_point_mixup.py L15-72, lam ~
+    Beta(2,2)) and two polar sector swaps of a Waymo-shaped frame into a nuScenes-shaped one (inter_domain_point_polarmix.py
+    L72-95, pi/2 sector), built once, outside the timer, with the K0 point kernels; the reference mixes in its dataset
+    workers, i.e. also on the input side of the step."""
+    from toda_b200.pcdet_plugin import processor as GP
+    f = synth.CONFIGS["toda_stage2"]["num_features"]
+    rng = np.random.default_rng(40000 + first)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a[:, :f])).to(device)    # noqa: E731
+    out = []
+    for i in range(FRAMES_PER_GPU):
+        a = synth.make_frame("toda_stage2", first * 3 + 3 * i)
+        if i % 2 == 0:
+            b = synth.make_frame("toda_stage2", first * 3 + 3 * i + 1)
+            lam = float(rng.beta(2.0, 2.0))
+            m = GP.mixup_points(t(a), t(b), lam, rng.permutation(a.shape[0]), rng.permutation(b.shape[0]))
+        else:
+            w = synth.make_frame("waymo_010", first + i)
+            s0 = float(rng.random() * np.pi * 2 - np.pi)
+            m = GP.polar_swap_points(t(a), t(w), s0, s0 + np.pi / 2)
+        out.append(m.cpu().numpy())
+    return out
+
+
+def host_batches(rank, n_batches, device=None):
+    """Pinned host copies of collated `points` [b,x,y,z,...] (dataset.py L173-178) + frame offsets."""
+    wl = WORKLOADS[WORKLOAD]
     out = []
     for j in range(n_batches):
         first = (rank * POOL + j) * FRAMES_PER_GPU
-        frames, collated = synth.make_batch(WORKLOAD, FRAMES_PER_GPU, first_frame=first)
+        if wl.get("mixed"):
+            frames = _stage2_frames(first, device)
+            collated = np.concatenate([np.pad(f, ((0, 0), (1, 0)), mode="constant", constant_values=i) for i, f in enumerate(frames)])
+        else:
+            frames, collated = synth.make_batch(wl["cfg"], FRAMES_PER_GPU, first_frame=first)
         offs = np.cumsum([0] + [f.shape[0] for f in frames]).astype(np.int32)
-        out.append((torch.from_numpy(collated).pin_memory(), torch.from_numpy(offs).pin_memory()))
+        out.append((torch.from_numpy(np.ascontiguousarray(collated, dtype=np.float32)).pin_memory(), torch.from_numpy(offs).pin_memory()))
     return out
 
 
@@ -175,7 +219,8 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(device)
     vfe, net, hc = build_hot_path(device, args.precision)
     bucket = FlatGradBucket(net.parameters())
-    hosts = host_batches(rank, POOL)
+    train = WORKLOADS[WORKLOAD]["train"]
+    hosts = host_batches(rank, POOL, device)
     devs = [(p.to(device), o.to(device)) for p, o in hosts]
     cot = None
 
@@ -186,17 +231,19 @@ def run_ours(args, rank, world, local_rank):
         t0 = time.perf_counter()
         bucket.zero()
         bd = {"points": points, "point_frame_offsets": offsets, "batch_size": FRAMES_PER_GPU}
-        bd = vfe(bd)
-        t1 = time.perf_counter()
-        bd = hc(net(bd))
+        with torch.set_grad_enabled(train):
+            bd = vfe(bd)
+            t1 = time.perf_counter()
+            bd = hc(net(bd))
         t2 = time.perf_counter()
         sf = bd["spatial_features"]
         if cot is None:
             cot = torch.randn(sf.shape, device=device, generator=torch.Generator(device=device).manual_seed(1)) / sf.numel()
         loss = (sf * cot).sum()
-        loss.backward()
-        if reduce:
-            bucket.all_reduce_mean()
+        if train:
+            loss.backward()
+            if reduce:
+                bucket.all_reduce_mean()
         if trace is not None:
             t3 = time.perf_counter()
             trace.append((round((t1 - t0) * 1e3, 2), round((t2 - t1) * 1e3, 2), round((t3 - t2) * 1e3, 2)))
@@ -246,12 +293,14 @@ def run_ours(args, rank, world, local_rank):
     def back(handle, reduce=True):
         t0 = time.perf_counter()
         bucket.zero()
-        bd = hc(net(pipe.consume(handle)))
+        with torch.set_grad_enabled(train):
+            bd = hc(net(pipe.consume(handle)))
         t1 = time.perf_counter()
         loss = (bd["spatial_features"] * cot).sum()
-        loss.backward()
-        if reduce:
-            bucket.all_reduce_mean()
+        if train:
+            loss.backward()
+            if reduce:
+                bucket.all_reduce_mean()
         if trace is not None:
             trace.append(("back", round((t1 - t0) * 1e3, 2), round((time.perf_counter() - t1) * 1e3, 2)))
         return loss, bd
@@ -343,15 +392,14 @@ def run_ours(args, rank, world, local_rank):
     loss, bd = step(*devs[0], reduce=False)     # rank 0 only: no collective inside this pass
     prof = ops.profile_end()
     roof, layers = roofline_from_profile(prof, bd, peaks, ms / args.steps)
-    line = dict(metric=METRIC, value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+    line = dict(metric=WORKLOADS[WORKLOAD]["metric"], value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32" if args.precision == "fp32" else "bf16", data="synthetic",
-                config=dict(workload="BASELINE.json configs[2]: CenterPoint VoxelResBackBone8x fwd+bwd, nuScenes-shaped 10-sweep "
-                                     "frames, 0.075 m voxels, grid 1440x1440x41, batch 4/GPU, train-mode BN, K=10, max_voxels 120000",
+                config=dict(workload=WORKLOADS[WORKLOAD]["desc"], workload_key=WORKLOAD,
                             frames_per_gpu=FRAMES_PER_GPU, points_per_frame=int(hosts[0][0].shape[0] / FRAMES_PER_GPU),
                             voxels_per_frame=int(bd["voxel_coords"].shape[0] / FRAMES_PER_GPU), conv_precision=args.precision,
                             l2="inputs rotate over %d pre-staged batches and each step streams >1 GB of activations (>> 126 MB L2)" % POOL,
-                            parallelism=f"dp{world} (frame-sharded, flat-bucket grad all-reduce)"),
+                            parallelism=f"dp{world} (frame-sharded" + (", bucketed grad all-reduce overlapped with backward)" if train else ", no collective: forward only)")),
                 clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roof, roofline_layers=layers)
     return line
 
@@ -461,14 +509,14 @@ def cpu_step_time(n_frames, steps, warmup):
     fwd+bwd + HeightCompression through the oracle's pure-PyTorch sparse conv (all host threads)."""
     from oracle import voxelize as OV
     from tests import parity_utils as PU
-    cfg = synth.CONFIGS[WORKLOAD]
+    cfg = synth.CONFIGS[WORKLOADS[WORKLOAD]["cfg"]]
     grid = synth.grid_size_xyz(cfg["pc_range"], cfg["voxel_size"])
     torch.manual_seed(666)
     net = PU.oracle_backbones()["VoxelResBackBone8x"](Cfg(), cfg["num_features"], grid)
     net.train()
     gens = [OV.Point2VoxelCPU3d(cfg["voxel_size"], cfg["pc_range"], cfg["num_features"], cfg["max_points"], cfg["max_voxels"]["train"])
             for _ in range(n_frames)]
-    frames = [synth.make_frame(WORKLOAD, i) for i in range(n_frames)]
+    frames = [synth.make_frame(WORKLOADS[WORKLOAD]["cfg"], i) for i in range(n_frames)]
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
@@ -512,7 +560,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("TODA_CONV_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="nus_0075", choices=sorted(WORKLOADS),
+                    help="default = BASELINE.json configs[2]; waymo_second = configs[1]; toda_stage2 = configs[3]")
     args = ap.parse_args()
+    global WORKLOAD, METRIC
+    WORKLOAD = args.workload
+    METRIC = WORKLOADS[WORKLOAD]["metric"]
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -531,7 +584,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     line = run_ours(args, rank, world, local_rank)
     if rank == 0:
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and WORKLOAD == "nus_0075":
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
             sec, nvox = cpu_step_time(1, 1, 0)

@@ -201,7 +201,10 @@ int toda_spconv_fwd_plan(const float *x, const void *x_bf16, int n_in, int cin, 
                          const float *w, int cout, const float *bias, const float *addend, float *y,
                          const int32_t *out_rows, const uint32_t *tile_masks, const uint16_t *plan_lidx,
                          const int32_t *plan_rows, const int32_t *plan_cnt, int plan_groups, int plan_cap, double *bn_sums,
-                         int precision, void *workspace, size_t workspace_bytes, void *stream);
+                         const void *w_bf16, int precision, void *workspace, size_t workspace_bytes, void *stream);
+/* w_bf16 (optional, may be NULL): the weights already converted for the tensor-core kernels by toda_weight_kmajor_bf16
+ * ([cout][kvol*max(cin,16)] bf16), so that a caller that caches them per optimizer step saves the conversion per call. */
+int toda_weight_kmajor_bf16(const float *w, int kvol, int cin, int cout, void *w_bf16, void *stream);
 size_t toda_spconv_wgrad_workspace_bytes(int n_in, int n_out, int kvol, int cin, int cout, int precision);
 int toda_spconv_wgrad(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
                       const float *dy, const void *dy_bf16, int cout, float *dw_param, void *workspace,
@@ -234,6 +237,42 @@ int toda_bn_bwd(const float *da, const float *a, const float *y, int n, int chan
 /* column sums: dbias[c] = sum_rows dy[:,c] */
 int toda_col_sum(const float *dy, int n, int channels, float *out, void *workspace, size_t workspace_bytes,
                  void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * One call per backbone layer: conv -> BatchNorm1d (+ residual) (+ ReLU) forward, and its backward
+ * (BN backward -> dgrad (+ residual-branch gradient) -> wgrad -> bias gradient): `post_act_block` /
+ * `SparseBasicBlock` (spconv_backbone.py L8-27, L30-66) as the host sees them.  Same kernels as the
+ * individual entry points above, sequenced in C so that the Python host pays one call per layer.
+ *   stats: float[4*cout] = scale, shift, save_mean, save_rstd (mean / rstd rows unused in eval mode)
+ *   sums : double[2*cout] scratch for the conv epilogue's statistics (training mode, tensor-core kernel)
+ * Pointers marked optional may be NULL.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    const float *x; const void *x_bf16; int n_in, cin; const int32_t *nbr; int n_out, kvol;
+    const float *w; const void *w_bf16 /* optional */; int cout; const float *bias /* optional */;
+    const uint32_t *tile_masks /* optional */;
+    const uint16_t *plan_lidx /* optional */; const int32_t *plan_rows; const int32_t *plan_cnt; int plan_groups, plan_cap;
+    int precision; void *conv_ws; size_t conv_ws_bytes;
+    const float *gamma; const float *beta; float eps, momentum; float *running_mean; float *running_var; int training;
+    const float *residual /* optional */; int relu;
+    float *y; double *sums; float *stats; float *a; void *a_bf16 /* optional */;
+    void *bn_ws; size_t bn_ws_bytes;
+} toda_layer_fwd_args;
+typedef struct {
+    const float *da; const float *a_mask; const float *y; int n_out, cout; const float *gamma; const float *mean; const float *rstd;
+    int relu, training; float *dy; void *dy_bf16 /* optional */; float *dres /* optional */; float *dgamma; float *dbeta;
+    void *bn_ws; size_t bn_ws_bytes;
+    const float *x; const void *x_bf16 /* optional */; int n_in, cin, kvol;
+    int need_dx; const int32_t *dgrad_nbr; const float *wt; const void *wt_bf16 /* optional */;
+    const int32_t *dgrad_out_rows /* optional */; const uint32_t *dgrad_masks /* optional */;
+    const uint16_t *dplan_lidx /* optional */; const int32_t *dplan_rows; const int32_t *dplan_cnt; int dplan_groups, dplan_cap;
+    const float *addend /* optional */; float *dx;
+    int need_dw; const int32_t *nbr_fwd; float *dw; void *wgrad_ws; size_t wgrad_ws_bytes;
+    int need_db; float *db;
+    int precision; void *conv_ws; size_t conv_ws_bytes;
+} toda_layer_bwd_args;
+int toda_layer_fwd(const toda_layer_fwd_args *args, void *stream);
+int toda_layer_bwd(const toda_layer_bwd_args *args, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * K9 HeightCompression: pcdet/models/backbones_2d/map_to_bev/height_compression.py L20-25

@@ -45,7 +45,10 @@ SIGNATURES = {
     "toda_tile_plan_capacity": (c_int, [c_int]),
     "toda_table_tile_plan": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "toda_spconv_fwd_plan": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
-                                     c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp, c_sz, c_vp]),
+                                     c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_sz, c_vp]),
+    "toda_weight_kmajor_bf16": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp]),
+    "toda_layer_fwd": (c_int, [c_vp, c_vp]),
+    "toda_layer_bwd": (c_int, [c_vp, c_vp]),
     "toda_spconv_wgrad_workspace_bytes": (c_sz, [c_int] * 6),
     "toda_spconv_wgrad": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_sz, c_int, c_vp]),
     "toda_bn_workspace_bytes": (c_sz, [c_int]),
@@ -61,6 +64,33 @@ SIGNATURES = {
     "toda_bev_scatter_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "toda_gather_rows": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp]),
 }
+
+
+
+class LayerFwdArgs(ctypes.Structure):
+    """toda_layer_fwd_args (include/toda_b200.h)."""
+    _fields_ = [("x", c_vp), ("x_bf16", c_vp), ("n_in", c_int), ("cin", c_int), ("nbr", c_vp), ("n_out", c_int), ("kvol", c_int),
+                ("w", c_vp), ("w_bf16", c_vp), ("cout", c_int), ("bias", c_vp), ("tile_masks", c_vp),
+                ("plan_lidx", c_vp), ("plan_rows", c_vp), ("plan_cnt", c_vp), ("plan_groups", c_int), ("plan_cap", c_int),
+                ("precision", c_int), ("conv_ws", c_vp), ("conv_ws_bytes", c_sz),
+                ("gamma", c_vp), ("beta", c_vp), ("eps", c_f32), ("momentum", c_f32), ("running_mean", c_vp), ("running_var", c_vp),
+                ("training", c_int), ("residual", c_vp), ("relu", c_int),
+                ("y", c_vp), ("sums", c_vp), ("stats", c_vp), ("a", c_vp), ("a_bf16", c_vp), ("bn_ws", c_vp), ("bn_ws_bytes", c_sz)]
+
+
+class LayerBwdArgs(ctypes.Structure):
+    """toda_layer_bwd_args (include/toda_b200.h)."""
+    _fields_ = [("da", c_vp), ("a_mask", c_vp), ("y", c_vp), ("n_out", c_int), ("cout", c_int), ("gamma", c_vp), ("mean", c_vp),
+                ("rstd", c_vp), ("relu", c_int), ("training", c_int), ("dy", c_vp), ("dy_bf16", c_vp), ("dres", c_vp), ("dgamma", c_vp),
+                ("dbeta", c_vp), ("bn_ws", c_vp), ("bn_ws_bytes", c_sz),
+                ("x", c_vp), ("x_bf16", c_vp), ("n_in", c_int), ("cin", c_int), ("kvol", c_int),
+                ("need_dx", c_int), ("dgrad_nbr", c_vp), ("wt", c_vp), ("wt_bf16", c_vp), ("dgrad_out_rows", c_vp), ("dgrad_masks", c_vp),
+                ("dplan_lidx", c_vp), ("dplan_rows", c_vp), ("dplan_cnt", c_vp), ("dplan_groups", c_int), ("dplan_cap", c_int),
+                ("addend", c_vp), ("dx", c_vp),
+                ("need_dw", c_int), ("nbr_fwd", c_vp), ("dw", c_vp), ("wgrad_ws", c_vp), ("wgrad_ws_bytes", c_sz),
+                ("need_db", c_int), ("db", c_vp),
+                ("precision", c_int), ("conv_ws", c_vp), ("conv_ws_bytes", c_sz)]
+
 
 _lib = None
 

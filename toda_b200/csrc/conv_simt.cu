@@ -9,7 +9,7 @@
 int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *w,
                 int cout, const float *bias, float *y, const int32_t *out_rows, const uint32_t *tile_masks, double *bn_sums,
                 void *workspace, size_t workspace_bytes,
-                cudaStream_t st, const TilePlan *plan, const float *addend);
+                cudaStream_t st, const TilePlan *plan, const float *addend, const void *w_bf16);
 size_t conv_tc_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol);
 int conv_tc_wgrad(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
                   const float *dy, const void *dy_bf16, int cout, float *dw_param, void *workspace, size_t workspace_bytes,
@@ -29,7 +29,8 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_f32_kernel(const float *__r
                                                                 const int *__restrict__ nbr, int n_out, int kvol,
                                                                 const float *__restrict__ w, int cout,
                                                                 const float *__restrict__ bias, float *__restrict__ y,
-                                                                const int *__restrict__ out_rows /* optional */) {
+                                                                const int *__restrict__ out_rows /* optional */,
+                                                                const float *__restrict__ addend /* optional */) {
     static_assert((BM / 4) * (BN / 4) == kThreads, "4x4 micro-tiles must cover the CTA tile");
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN + 4];
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_f32_kernel(const float *__r
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int c = col0 + tx * 4 + j;
-            if (c < cout) y[(size_t)orow * cout + c] = acc[i][j] + (bias ? __ldg(bias + c) : 0.f);
+            if (c < cout) y[(size_t)orow * cout + c] = acc[i][j] + (bias ? __ldg(bias + c) : 0.f) + (addend ? __ldg(addend + (size_t)orow * cout + c) : 0.f);
         }
     }
 }
@@ -267,30 +268,30 @@ extern "C" size_t toda_spconv_fwd_workspace_bytes(int n_in, int cin, int cout, i
 static int spconv_fwd_impl(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
                            const float *w, int cout, const float *bias, float *y, const int32_t *out_rows,
                            const uint32_t *tile_masks, double *bn_sums, int precision, void *workspace, size_t workspace_bytes,
-                           void *stream, const TilePlan *plan, const float *addend);
+                           void *stream, const TilePlan *plan, const float *addend, const void *w_bf16);
 
 extern "C" int toda_spconv_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
                                const float *w, int cout, const float *bias, float *y, const int32_t *out_rows,
                                const uint32_t *tile_masks, double *bn_sums, int precision,
                                void *workspace, size_t workspace_bytes, void *stream) {
     return spconv_fwd_impl(x, x_bf16, n_in, cin, nbr, n_out, kvol, w, cout, bias, y, out_rows, tile_masks, bn_sums, precision, workspace,
-                           workspace_bytes, stream, nullptr, nullptr);
+                           workspace_bytes, stream, nullptr, nullptr, nullptr);
 }
 
 extern "C" int toda_spconv_fwd_plan(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
                                     const float *w, int cout, const float *bias, const float *addend, float *y,
                                     const int32_t *out_rows, const uint32_t *tile_masks, const uint16_t *plan_lidx,
                                     const int32_t *plan_rows, const int32_t *plan_cnt, int plan_groups, int plan_cap, double *bn_sums,
-                                    int precision, void *workspace, size_t workspace_bytes, void *stream) {
+                                    const void *w_bf16, int precision, void *workspace, size_t workspace_bytes, void *stream) {
     TilePlan plan{plan_lidx, plan_rows, plan_cnt, plan_groups, plan_cap};
     return spconv_fwd_impl(x, x_bf16, n_in, cin, nbr, n_out, kvol, w, cout, bias, y, out_rows, tile_masks, bn_sums, precision, workspace,
-                           workspace_bytes, stream, plan_lidx ? &plan : nullptr, addend);
+                           workspace_bytes, stream, plan_lidx ? &plan : nullptr, addend, w_bf16);
 }
 
 static int spconv_fwd_impl(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
                            const float *w, int cout, const float *bias, float *y, const int32_t *out_rows,
                            const uint32_t *tile_masks, double *bn_sums, int precision, void *workspace, size_t workspace_bytes,
-                           void *stream, const TilePlan *plan, const float *addend) {
+                           void *stream, const TilePlan *plan, const float *addend, const void *w_bf16) {
     TODA_CHECK_ARG(n_in >= 0 && n_out >= 0 && cin > 0 && cout > 0 && kvol > 0, "spconv_fwd: bad sizes");
     if (n_out == 0) return TODA_OK;
     TODA_CHECK_ARG(x && nbr && w && y, "spconv_fwd: null pointer");
@@ -300,18 +301,17 @@ static int spconv_fwd_impl(const float *x, const void *x_bf16, int n_in, int cin
     // Cout in {16,32,64,128}; anything else (e.g. the dgrad of the 4/5-channel input layer) runs on the FFMA kernel.
     if (precision == TODA_CONV_BF16 && conv_tc_supported(cin, cout, kvol))
         return conv_tc_fwd(x, x_bf16, n_in, cin, nbr, n_out, kvol, w, cout, bias, y, out_rows, tile_masks, bn_sums, workspace,
-                           workspace_bytes, st, plan, addend);
-    TODA_CHECK_ARG(!addend, "spconv_fwd: a fused addend needs the tensor-core tile-plan kernel for this shape");
+                           workspace_bytes, st, plan, addend, w_bf16);
     TODA_CHECK_ARG(!bn_sums, "spconv_fwd: fused BatchNorm statistics need the tensor-core kernel for this shape");
     if (cout <= 16) {
         dim3 grid(ceil_div(n_out, 256), ceil_div(cout, 16));
-        conv_fwd_f32_kernel<256, 16><<<grid, kThreads, 0, st>>>(x, cin, nbr, n_out, kvol, w, cout, bias, y, out_rows);
+        conv_fwd_f32_kernel<256, 16><<<grid, kThreads, 0, st>>>(x, cin, nbr, n_out, kvol, w, cout, bias, y, out_rows, addend);
     } else if (cout <= 32) {
         dim3 grid(ceil_div(n_out, 128), ceil_div(cout, 32));
-        conv_fwd_f32_kernel<128, 32><<<grid, kThreads, 0, st>>>(x, cin, nbr, n_out, kvol, w, cout, bias, y, out_rows);
+        conv_fwd_f32_kernel<128, 32><<<grid, kThreads, 0, st>>>(x, cin, nbr, n_out, kvol, w, cout, bias, y, out_rows, addend);
     } else {
         dim3 grid(ceil_div(n_out, 64), ceil_div(cout, 64));
-        conv_fwd_f32_kernel<64, 64><<<grid, kThreads, 0, st>>>(x, cin, nbr, n_out, kvol, w, cout, bias, y, out_rows);
+        conv_fwd_f32_kernel<64, 64><<<grid, kThreads, 0, st>>>(x, cin, nbr, n_out, kvol, w, cout, bias, y, out_rows, addend);
     }
     TODA_LAUNCH_OK();
     return TODA_OK;

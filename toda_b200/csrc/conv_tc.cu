@@ -167,7 +167,8 @@ template <int CIN, int COUT, int KB>
 __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_bfloat16 *__restrict__ xb,
                                                                      const int *__restrict__ nbr, int n_out, int kvol,
                                                                      const __grid_constant__ CUtensorMap map_w /*[COUT][kvol*CIN] bf16*/,
-                                                                     const float *__restrict__ bias, float *__restrict__ y,
+                                                                     const float *__restrict__ bias, const float *__restrict__ addend /* optional */,
+                                                                     float *__restrict__ y,
                                                                      const int *__restrict__ out_rows /* optional */,
                                                                      const uint32_t *__restrict__ tile_masks /* optional */,
                                                                      double *__restrict__ bn_sums, int num_tiles,
@@ -384,6 +385,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) conv_tc_fwd_kernel(const __nv_
 #pragma unroll
                 for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + n0 + j) : 0.f);
                 if (row < n_out) {
+                    if (addend) {
+                        const float4 *ad = (const float4 *)(addend + (size_t)orow * COUT + n0);
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            const float4 a4 = __ldg(ad + qq);
+                            o[4 * qq] += a4.x; o[4 * qq + 1] += a4.y; o[4 * qq + 2] += a4.z; o[4 * qq + 3] += a4.w;
+                        }
+                    }
                     float4 *dst = (float4 *)(y + (size_t)orow * COUT + n0);
 #pragma unroll
                     for (int qq = 0; qq < 4; ++qq) dst[qq] = make_float4(o[4 * qq], o[4 * qq + 1], o[4 * qq + 2], o[4 * qq + 3]);
@@ -501,7 +510,7 @@ extern "C" int toda_table_tile_masks(const int32_t *nbr, int n_out, int kvol, ui
 static inline int pad16(int c) { return c < 16 ? 16 : c; }
 
 int conv_tma_fwd(const void *xb, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const void *wb, int cout,
-                 const float *bias, float *y, const int32_t *out_rows, const uint32_t *tile_masks, double *bn_sums,
+                 const float *bias, const float *addend, float *y, const int32_t *out_rows, const uint32_t *tile_masks, double *bn_sums,
                  cudaStream_t st);
 
 // development aid: device buffer (8 x 256 int64: clock64 samples per chunk / per tile) filled by CTA 0 of the cp.async forward kernel
@@ -511,6 +520,16 @@ long long *conv_tc_debug_timeline() { return g_dbg_timeline; }
 static int g_dbg_mode = 0;
 extern "C" void toda_debug_set_mode(int m) { g_dbg_mode = m; }
 int conv_tc_debug_mode() { return g_dbg_mode; }
+
+// w [kvol][cin][cout] fp32 -> [cout][kvol*max(cin,16)] bf16, the B operand of the tensor-core kernels (cacheable by the caller)
+extern "C" int toda_weight_kmajor_bf16(const float *w, int kvol, int cin, int cout, void *w_bf16, void *stream) {
+    TODA_CHECK_ARG(w && w_bf16 && kvol > 0 && cin > 0 && cout > 0, "weight_kmajor_bf16: bad args");
+    const int cp = cin < 16 ? 16 : cin;
+    weight_to_kmajor_bf16_kernel<<<wave_grid((int64_t)kvol * cp * cout, 256), 256, 0, (cudaStream_t)stream>>>(w, kvol, cin, cp, cout,
+                                                                                                            (__nv_bfloat16 *)w_bf16);
+    TODA_LAUNCH_OK();
+    return TODA_OK;
+}
 
 bool conv_tc_supported(int cin, int cout, int kvol) {
     bool cin_ok = (cin >= 1 && cin < 16) || cin == 16 || cin == 32 || cin == 64 || cin == 128;
@@ -525,7 +544,7 @@ size_t conv_tc_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol) {
 int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *w,
                 int cout, const float *bias, float *y, const int32_t *out_rows, const uint32_t *tile_masks, double *bn_sums,
                 void *workspace, size_t workspace_bytes,
-                cudaStream_t st, const TilePlan *plan, const float *addend) {
+                cudaStream_t st, const TilePlan *plan, const float *addend, const void *w_bf16) {
     size_t need = conv_tc_fwd_workspace_bytes(n_in, cin, cout, kvol);
     if (!workspace || workspace_bytes < need) {
         toda_set_error("spconv_fwd(bf16): workspace %zu < required %zu bytes", workspace_bytes, need);
@@ -546,8 +565,12 @@ int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int
         f32_to_bf16_pad_kernel<<<wave_grid((int64_t)n_in * cp, 256), 256, 0, st>>>(x, n_in, cin, cp, xb);
         TODA_LAUNCH_OK();
     }
-    weight_to_kmajor_bf16_kernel<<<wave_grid((int64_t)kvol * cp * cout, 256), 256, 0, st>>>(w, kvol, cin, cp, cout, wb);
-    TODA_LAUNCH_OK();
+    if (w_bf16) {
+        wb = (__nv_bfloat16 *)w_bf16;      // caller caches the K-major bf16 weights (toda_weight_kmajor_bf16)
+    } else {
+        weight_to_kmajor_bf16_kernel<<<wave_grid((int64_t)kvol * cp * cout, 256), 256, 0, st>>>(w, kvol, cin, cp, cout, wb);
+        TODA_LAUNCH_OK();
+    }
     cin = cp;
     if (bn_sums) TODA_CUDA_OK(cudaMemsetAsync(bn_sums, 0, 2 * (size_t)cout * sizeof(double), st));
     // operand feed, chosen by shape from measurements on B200 (profiles/r01_feed_ab.md): TMA (gather4 rows + tiled
@@ -560,15 +583,11 @@ int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int
     // (TODA_TC_FEED=tma|cpasync keeps the round-1 kernels for A/B measurements)
     if (feed == 2 && conv_ts_supported(cin, cout, kvol, plan))
         return conv_ts_fwd(xb, n_in, cin, nbr, n_out, kvol, *plan, wb, cout, bias, addend, y, out_rows, tile_masks, bn_sums, st);
-    if (addend) {
-        toda_set_error("spconv_fwd: a fused addend needs the tile-plan kernel (plan missing or shape unsupported)");
-        return TODA_ERR_UNSUPPORTED;
-    }
     if (feed == 1 || (feed == 2 && cin == 128 && cout == 128))
         {
         // (raster-order masks skip ~17 % of the 128-channel chunks but measured slower on this kernel -- the skipped chunks
         // unbalance the round-robin of its four issuing warps; class-sorted dgrad rows, where most chunks vanish, keep them)
-        return conv_tma_fwd(xb, n_in, cin, nbr, n_out, kvol, wb, cout, bias, y, out_rows, out_rows ? tile_masks : nullptr, bn_sums, st);
+        return conv_tma_fwd(xb, n_in, cin, nbr, n_out, kvol, wb, cout, bias, addend, y, out_rows, out_rows ? tile_masks : nullptr, bn_sums, st);
     }
     int num_tiles = ceil_div(n_out, kTileM);
     int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;   // persistent: one CTA per SM walks the tiles
@@ -585,7 +604,7 @@ int conv_tc_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int
             TODA_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_kernel<CI, CO, KB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
             attr_set = true;                                                                                                 \
         }                                                                                                                    \
-        conv_tc_fwd_kernel<CI, CO, KB_><<<grid, kFwdThreads, smem, st>>>(xb, nbr, n_out, kvol, map_w, bias, y, out_rows, tile_masks, bn_sums, num_tiles, g_dbg_timeline); \
+        conv_tc_fwd_kernel<CI, CO, KB_><<<grid, kFwdThreads, smem, st>>>(xb, nbr, n_out, kvol, map_w, bias, addend, y, out_rows, tile_masks, bn_sums, num_tiles, g_dbg_timeline); \
     } while (0)
 #define LAUNCH_TC_CO(CI)                                                                                 \
     switch (cout) {                                                                                      \

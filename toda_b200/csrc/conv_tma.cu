@@ -135,7 +135,8 @@ template <int CIN, int COUT>
 __global__ void __launch_bounds__(kThreads, 1) conv_tma_fwd_kernel(const __grid_constant__ CUtensorMap map_x,
                                                                    const __grid_constant__ CUtensorMap map_w,
                                                                    const int *__restrict__ nbr, int n_in, int n_out, int kvol,
-                                                                   const float *__restrict__ bias, float *__restrict__ y,
+                                                                   const float *__restrict__ bias, const float *__restrict__ addend /* optional */,
+                                                                   float *__restrict__ y,
                                                                    const int *__restrict__ out_rows /* optional */,
                                                                    const uint32_t *__restrict__ tile_masks /* optional */,
                                                                    double *__restrict__ bn_sums, int num_tiles) {
@@ -285,6 +286,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_fwd_kernel(const __grid_
 #pragma unroll
                 for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + n0 + j) : 0.f);
                 if (row < n_out) {
+                    if (addend) {
+                        const float4 *ad = (const float4 *)(addend + (size_t)orow * COUT + n0);
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            const float4 a4 = __ldg(ad + qq);
+                            o[4 * qq] += a4.x; o[4 * qq + 1] += a4.y; o[4 * qq + 2] += a4.z; o[4 * qq + 3] += a4.w;
+                        }
+                    }
                     float4 *dst = (float4 *)(y + (size_t)orow * COUT + n0);
 #pragma unroll
                     for (int qq = 0; qq < 4; ++qq) dst[qq] = make_float4(o[4 * qq], o[4 * qq + 1], o[4 * qq + 2], o[4 * qq + 3]);
@@ -368,7 +377,7 @@ int make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, uint
 
 template <int CIN, int COUT>
 int launch(const __nv_bfloat16 *xb, int n_in, const int32_t *nbr, int n_out, int kvol, const __nv_bfloat16 *wb, const float *bias,
-           float *y, const int32_t *out_rows, const uint32_t *tile_masks, double *bn_sums, cudaStream_t st) {
+           const float *addend, float *y, const int32_t *out_rows, const uint32_t *tile_masks, double *bn_sums, cudaStream_t st) {
     using C = Cfg<CIN, COUT>;
     CUtensorMap mx, mw;
     if (int rc = make_map(&mx, xb, (uint64_t)n_in, CIN, 1, C::kRowElems)) return rc;              // gather4: box = one row
@@ -380,7 +389,7 @@ int launch(const __nv_bfloat16 *xb, int n_in, const int32_t *nbr, int n_out, int
         TODA_CUDA_OK(cudaFuncSetAttribute(conv_tma_fwd_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
         attr_set = true;
     }
-    conv_tma_fwd_kernel<CIN, COUT><<<grid, kThreads, C::kSmem, st>>>(mx, mw, nbr, n_in, n_out, kvol, bias, y, out_rows, tile_masks, bn_sums, num_tiles);
+    conv_tma_fwd_kernel<CIN, COUT><<<grid, kThreads, C::kSmem, st>>>(mx, mw, nbr, n_in, n_out, kvol, bias, addend, y, out_rows, tile_masks, bn_sums, num_tiles);
     TODA_LAUNCH_OK();
     return TODA_OK;
 }
@@ -393,15 +402,15 @@ int conv_tma_make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t c
 
 // xb: bf16 [n_in][cin], wb: bf16 [cout][kvol*cin]; cin, cout in {16,32,64,128}
 int conv_tma_fwd(const void *xb, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const void *wb, int cout,
-                 const float *bias, float *y, const int32_t *out_rows, const uint32_t *tile_masks, double *bn_sums,
+                 const float *bias, const float *addend, float *y, const int32_t *out_rows, const uint32_t *tile_masks, double *bn_sums,
                  cudaStream_t st) {
     const __nv_bfloat16 *x = (const __nv_bfloat16 *)xb, *w = (const __nv_bfloat16 *)wb;
 #define CASE_CO(CI)                                                                                    \
     switch (cout) {                                                                                    \
-        case 16: return launch<CI, 16>(x, n_in, nbr, n_out, kvol, w, bias, y, out_rows, tile_masks, bn_sums, st);                     \
-        case 32: return launch<CI, 32>(x, n_in, nbr, n_out, kvol, w, bias, y, out_rows, tile_masks, bn_sums, st);                     \
-        case 64: return launch<CI, 64>(x, n_in, nbr, n_out, kvol, w, bias, y, out_rows, tile_masks, bn_sums, st);                     \
-        case 128: return launch<CI, 128>(x, n_in, nbr, n_out, kvol, w, bias, y, out_rows, tile_masks, bn_sums, st);                   \
+        case 16: return launch<CI, 16>(x, n_in, nbr, n_out, kvol, w, bias, addend, y, out_rows, tile_masks, bn_sums, st);                     \
+        case 32: return launch<CI, 32>(x, n_in, nbr, n_out, kvol, w, bias, addend, y, out_rows, tile_masks, bn_sums, st);                     \
+        case 64: return launch<CI, 64>(x, n_in, nbr, n_out, kvol, w, bias, addend, y, out_rows, tile_masks, bn_sums, st);                     \
+        case 128: return launch<CI, 128>(x, n_in, nbr, n_out, kvol, w, bias, addend, y, out_rows, tile_masks, bn_sums, st);                   \
     }                                                                                                  \
     break;
     switch (cin) {

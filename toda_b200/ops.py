@@ -84,8 +84,15 @@ def _timed(name, **meta):
     return _Timed(name, meta) if _prof is not None else _NO_TIMER
 
 
+_raw_stream = torch._C._cuda_getCurrentRawStream     # (device index) -> cudaStream_t as int: ~0.2 us, torch.cuda.current_stream() ~8 us
+
+
+def _stream_id(device=None):
+    return _raw_stream(torch.cuda.current_device() if device is None or device.index is None else device.index)
+
+
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(_raw_stream(torch.cuda.current_device()))
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -109,7 +116,7 @@ def _workspace(tag, nbytes, device, zero=False):
     """Grow-only cached scratch buffers (caller-owned memory in the ABI's terms).  One buffer per (tag, device, STREAM):
     the input pipeline runs the front of batch i+1 on a side stream while the main stream may still use the same tag, and
     a block must never be shared (or regrown, which frees the old block into another stream's pool) across streams."""
-    key = (tag, device.index, torch.cuda.current_stream(device).cuda_stream)
+    key = (tag, device.index, _stream_id(device))
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = (torch.zeros if zero else torch.empty)(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
@@ -274,7 +281,7 @@ class OccupancyIndex:
         nbytes = _C.lib().toda_index_bytes(self.batch, d, h, w)
         if nbytes == 0:
             raise RuntimeError(f"bad index dims {batch} {shape}")
-        self.key = (("index", tag, self.batch, d, h, w), device.index, torch.cuda.current_stream(device).cuda_stream)
+        self.key = (("index", tag, self.batch, d, h, w), device.index, _stream_id(device))
         self.buf = _workspace(self.key[0], nbytes, device, zero=True)
         self.coords = None
         self.frame_counts = None
@@ -542,22 +549,33 @@ def invalidate_weight_cache():
     _repack_cache.clear()
 
 
-def _repack(weight, transpose, mirror):
+def _repack(weight, transpose, mirror, want_bf16=False):
     """[kvol][Cin][Cout] (or transposed / k-mirrored) copy of a (Cout,kz,ky,kx,Cin) parameter, cached until the
-    parameter is modified (optimizer step bumps ._version; for `.data` writes see invalidate_weight_cache)."""
+    parameter is modified (optimizer step bumps ._version; for `.data` writes see invalidate_weight_cache).
+    want_bf16: -> (fp32 repack, K-major bf16 copy for the tensor-core kernels (toda_weight_kmajor_bf16), cached alongside)."""
     key = (id(weight), bool(transpose), bool(mirror))
     hit = _repack_cache.get(key)
     if hit is not None and hit[2]() is weight and hit[0] == weight._version and hit[3] == weight.data_ptr():
-        return hit[1]
-    cout, kvol, cin = weight.shape[0], weight.shape[1] * weight.shape[2] * weight.shape[3], weight.shape[4]
-    out = torch.empty((kvol, cout, cin) if transpose else (kvol, cin, cout), dtype=torch.float32, device=weight.device)
-    _C.check(_C.lib().toda_weight_repack(_p(weight), kvol, cin, cout, int(transpose), int(mirror), _p(out), _stream()),
-             "toda_weight_repack")
-    _count(1)
-    if len(_repack_cache) > 512:
-        _repack_cache.clear()
-    _repack_cache[key] = (weight._version, out, weakref.ref(weight), weight.data_ptr())
-    return out
+        out = hit[1]
+    else:
+        cout, kvol, cin = weight.shape[0], weight.shape[1] * weight.shape[2] * weight.shape[3], weight.shape[4]
+        out = torch.empty((kvol, cout, cin) if transpose else (kvol, cin, cout), dtype=torch.float32, device=weight.device)
+        _C.check(_C.lib().toda_weight_repack(_p(weight), kvol, cin, cout, int(transpose), int(mirror), _p(out), _stream()),
+                 "toda_weight_repack")
+        _count(1)
+        if len(_repack_cache) > 512:
+            _repack_cache.clear()
+        hit = [weight._version, out, weakref.ref(weight), weight.data_ptr(), None]
+        _repack_cache[key] = hit
+    if not want_bf16:
+        return out
+    if hit[4] is None:
+        kvol, ci, co = out.shape
+        wb = torch.empty((co, kvol * max(ci, 16)), dtype=torch.bfloat16, device=out.device)
+        _C.check(_C.lib().toda_weight_kmajor_bf16(_p(out), kvol, ci, co, _p(wb), _stream()), "toda_weight_kmajor_bf16")
+        _count(1)
+        hit[4] = wb
+    return out, hit[4]
 
 
 def _bf16_shadow_of(t):
@@ -569,7 +587,7 @@ def _bf16_shadow_of(t):
 
 
 def _conv_call(x, xb, cin, nbr, n_out, kvol, w, cout, bias, precision, what="conv_fwd", rb=None, bn_sums=None, y=None,
-               out_rows=None, tile_masks=None, plan=None, addend=None):
+               out_rows=None, tile_masks=None, plan=None, addend=None, w_bf16=None):
     """addend (optional, (n_out, cout) fp32): added to the result in the kernel's epilogue; only with a usable plan
     (see conv_plan_usable), otherwise the caller adds it."""
     if y is None:
@@ -580,15 +598,16 @@ def _conv_call(x, xb, cin, nbr, n_out, kvol, w, cout, bias, precision, what="con
     if precision != CONV_BF16:
         plan = None
     with _timed(what, n_in=x.shape[0], n_out=n_out, cin=cin, cout=cout, kvol=kvol, precision=precision, rb=id(rb)):
-        if plan is None:
-            assert addend is None
+        if plan is None and addend is None and w_bf16 is None:
             _C.check(L.toda_spconv_fwd(_p(x), _p(xb), x.shape[0], cin, _p(nbr), n_out, kvol, _p(w), cout, _p(bias), _p(y),
                                        _p(out_rows), _p(tile_masks), _p(bn_sums), precision, _p(ws), ws.numel() if ws is not None else 0,
                                        _stream()), "toda_spconv_fwd")
         else:
+            pl = plan
             _C.check(L.toda_spconv_fwd_plan(_p(x), _p(xb), x.shape[0], cin, _p(nbr), n_out, kvol, _p(w), cout, _p(bias),
-                                            _p(addend), _p(y), _p(out_rows), _p(tile_masks), _p(plan.lidx), _p(plan.rows),
-                                            _p(plan.cnt), plan.ngroups, plan.cap, _p(bn_sums), precision, _p(ws),
+                                            _p(addend), _p(y), _p(out_rows), _p(tile_masks), _p(pl.lidx) if pl else None,
+                                            _p(pl.rows) if pl else None, _p(pl.cnt) if pl else None, pl.ngroups if pl else 0,
+                                            pl.cap if pl else 0, _p(bn_sums), _p(w_bf16), precision, _p(ws),
                                             ws.numel() if ws is not None else 0, _stream()), "toda_spconv_fwd_plan")
     _count(1)
     return y
@@ -817,17 +836,135 @@ class _BNAct(torch.autograd.Function):
         return dy, dgamma, dbeta, None, None, None, None, None, dres, None, None, None
 
 
+def _vp(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _fused_ok(training, need_grad):
+    """The one-call-per-layer C path (toda_layer_fwd / toda_layer_bwd) is used unless a per-kernel profile pass or the
+    ReLU-mask test instrument is active, or a gradient is wanted through eval-mode BatchNorm (kept on the stepwise path)."""
+    return _prof is None and _relu_tape is None and (training or not need_grad)
+
+
+def _layer_forward(x, x_bf16, weight, bias, rb, precision, gamma, beta, running_mean, running_var, eps, momentum, training,
+                   residual, relu, want_bf16, need_grad=True):
+    """conv -> BN (+residual) (+ReLU).  -> (a, a_bf16, saved) with saved = (x, x_bf16, weight, y, a_mask, gamma, mean, rstd)."""
+    if not _fused_ok(training, need_grad):
+        y, sums, x, weight, x_bf16 = _conv_forward_impl(x, x_bf16, weight, bias, rb, precision, bool(training))
+        a, ab, y, mean, rstd, a_mask = _bn_forward_impl(y, gamma, beta, running_mean, running_var, eps, momentum, training,
+                                                        residual, relu, want_bf16, sums, need_grad)
+        return a, ab, (x, x_bf16, weight, y, a_mask, gamma, mean, rstd)
+    x = _need(x.contiguous(), torch.float32, "features")
+    weight = _need(weight.contiguous(), torch.float32, "weight")
+    cout, cin = weight.shape[0], weight.shape[4]
+    assert x.shape == (rb.n_in, cin), (x.shape, rb.n_in, cin)
+    if x_bf16 is not None and (precision != CONV_BF16 or x_bf16.shape != x.shape or x_bf16.dtype != torch.bfloat16
+                               or not x_bf16.is_contiguous()):
+        x_bf16 = None
+    L = _C.lib()
+    kvol, n_out, dev = rb.kvol, rb.n_out, x.device
+    tc = bool(L.toda_spconv_uses_tensor_cores(cin, cout, kvol, precision))
+    if tc:
+        w, wb = _repack(weight, False, False, True)
+    else:
+        w, wb = _repack(weight, False, False), None
+    y = torch.empty((n_out, cout), dtype=torch.float32, device=dev)
+    a = torch.empty_like(y)
+    ab = torch.empty((n_out, cout), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    small = torch.empty((8 * cout,), dtype=torch.float32, device=dev)       # scale, shift, mean, rstd | sums (2c doubles)
+    ws_bytes = L.toda_spconv_fwd_workspace_bytes(x.shape[0], cin, cout, kvol, precision)
+    ws = _workspace("conv", ws_bytes, dev) if ws_bytes else None
+    bws = _workspace("bn", L.toda_bn_workspace_bytes(cout), dev)
+    res = residual.contiguous() if residual is not None else None
+    b = bias.contiguous() if bias is not None else None
+    pl = rb.plan if precision == CONV_BF16 else None
+    sp = small.data_ptr()
+    args = _C.LayerFwdArgs(
+        x.data_ptr(), _vp(x_bf16), x.shape[0], cin, rb.nbr_fwd.data_ptr(), n_out, kvol, w.data_ptr(), _vp(wb), cout, _vp(b),
+        _vp(rb.tile_masks), _vp(pl.lidx) if pl else None, _vp(pl.rows) if pl else None, _vp(pl.cnt) if pl else None,
+        pl.ngroups if pl else 0, pl.cap if pl else 0, precision, _vp(ws), ws.numel() if ws is not None else 0,
+        gamma.data_ptr(), beta.data_ptr(), float(eps), float(momentum), _vp(running_mean), _vp(running_var), int(bool(training)),
+        _vp(res), int(bool(relu)), y.data_ptr(), sp + 16 * cout, sp, a.data_ptr(), _vp(ab), bws.data_ptr(), bws.numel())
+    _C.check(L.toda_layer_fwd(ctypes.byref(args), _stream()), "toda_layer_fwd")
+    _count(3 if tc else 4)
+    mean = small[2 * cout:3 * cout] if training else running_mean
+    rstd = small[3 * cout:4 * cout] if training else None
+    return a, ab, (x, x_bf16, weight, y, a, gamma, mean, rstd)
+
+
+def _layer_backward(da, saved, rb, precision, training, relu, has_res, has_bias, need_dx, need_dw, addend=None):
+    """-> (dx, dw, db, dgamma, dbeta, dres).  addend: a gradient to be ADDED to dx (fused into the dgrad epilogue)."""
+    x, xb, weight, y, a_mask, gamma, mean, rstd = saved
+    if not _fused_ok(training, True):
+        dy, dyb, dres, dgamma, dbeta = _bn_backward_impl(da, y, a_mask, gamma, mean, rstd, training, relu, has_res,
+                                                         precision == CONV_BF16)
+        dx, dw, db = _conv_backward_impl(dy, dyb, x, weight, xb, rb, precision, need_dx, need_dw, has_bias)
+        if addend is not None and dx is not None:
+            dx = dx + addend
+        return dx, dw, db, dgamma, dbeta, dres
+    L = _C.lib()
+    da = da.contiguous()
+    n_out, cout = y.shape
+    cin, kvol, dev = weight.shape[4], rb.kvol, y.device
+    bf16 = precision == CONV_BF16
+    dy = torch.empty_like(y)
+    dyb = torch.empty(y.shape, dtype=torch.bfloat16, device=dev) if bf16 else None
+    dres = torch.empty_like(y) if has_res else None
+    small = torch.empty((3 * cout,), dtype=torch.float32, device=dev)        # dgamma, dbeta, dbias
+    bws = _workspace("bn", L.toda_bn_workspace_bytes(cout), dev)
+    dx = dw = None
+    wt = wtb = None
+    nbr = out_rows = masks = pl = None
+    if need_dx:
+        tc = bool(L.toda_spconv_uses_tensor_cores(cout, cin, kvol, precision))
+        if tc:
+            wt, wtb = _repack(weight, True, rb.subm, True)
+        else:
+            wt = _repack(weight, True, rb.subm)
+        if rb.subm:
+            nbr, masks, pl = rb.nbr_fwd, rb.tile_masks, rb.plan
+        elif rb.dgrad_order is None:
+            nbr, pl = rb.nbr_bwd, rb.dgrad_plan
+        else:
+            nbr, out_rows, masks, pl = rb.nbr_bwd_sorted, rb.dgrad_order, rb.dgrad_tile_masks, rb.dgrad_plan
+        if not bf16:
+            pl = None
+        dx = torch.empty((rb.n_in, cin), dtype=torch.float32, device=dev)
+        if addend is not None:
+            addend = addend.contiguous()
+    ws_bytes = L.toda_spconv_fwd_workspace_bytes(n_out, cout, cin, kvol, precision) if need_dx else 0
+    ws = _workspace("conv", ws_bytes, dev) if ws_bytes else None
+    wws = None
+    if need_dw:
+        dw = torch.empty_like(weight)
+        wws = _workspace("wgrad", L.toda_spconv_wgrad_workspace_bytes(rb.n_in, n_out, kvol, cin, cout, precision), dev)
+    sp = small.data_ptr()
+    args = _C.LayerBwdArgs(
+        da.data_ptr(), a_mask.data_ptr(), y.data_ptr(), n_out, cout, gamma.data_ptr(), _vp(mean), _vp(rstd), int(relu), int(training),
+        dy.data_ptr(), _vp(dyb), _vp(dres), sp, sp + 4 * cout, bws.data_ptr(), bws.numel(),
+        x.data_ptr(), _vp(xb), rb.n_in, cin, kvol,
+        int(bool(need_dx)), _vp(nbr), _vp(wt), _vp(wtb), _vp(out_rows), _vp(masks),
+        _vp(pl.lidx) if pl else None, _vp(pl.rows) if pl else None, _vp(pl.cnt) if pl else None, pl.ngroups if pl else 0,
+        pl.cap if pl else 0, _vp(addend) if need_dx else None, _vp(dx),
+        int(bool(need_dw)), rb.nbr_fwd.data_ptr(), _vp(dw), _vp(wws), wws.numel() if wws is not None else 0,
+        int(bool(has_bias)), sp + 8 * cout, precision, _vp(ws), ws.numel() if ws is not None else 0)
+    _C.check(L.toda_layer_bwd(ctypes.byref(args), _stream()), "toda_layer_bwd")
+    _count(3 + (1 if need_dx else 0) + (2 if need_dw else 0) + (2 if has_bias else 0))
+    return dx, dw, (small[2 * cout:] if has_bias else None), small[:cout], small[cout:2 * cout], dres
+
+
 class _ConvBNAct(torch.autograd.Function):
-    """conv -> BatchNorm1d (+ residual) (+ ReLU) as ONE autograd node: half the Python / autograd-engine overhead per layer
-    of the two separate nodes, and the gradient between BN and conv (dy and its bf16 copy) never becomes a graph edge."""
+    """conv -> BatchNorm1d (+ residual) (+ ReLU) as ONE autograd node and ONE C call each way (toda_layer_fwd / _bwd): the
+    gradient between BN and conv (dy and its bf16 copy) never becomes a graph edge."""
 
     @staticmethod
     def forward(ctx, x, x_bf16, weight, bias, rb, precision, gamma, beta, running_mean, running_var, eps, momentum, training,
                 residual, relu, want_bf16):
-        y, sums, x, weight, x_bf16 = _conv_forward_impl(x, x_bf16, weight, bias, rb, precision, bool(training))
-        a, ab, y, mean, rstd, a_mask = _bn_forward_impl(y, gamma, beta, running_mean, running_var, eps, momentum, training,
-                                                        residual, relu, want_bf16, sums, True)
-        ctx.save_for_backward(x, weight, x_bf16, y, a_mask, gamma, mean, rstd)
+        need_grad = any(ctx.needs_input_grad)
+        a, ab, saved = _layer_forward(x, x_bf16, weight, bias, rb, precision, gamma, beta, running_mean, running_var, eps, momentum,
+                                      training, residual, relu, want_bf16, need_grad)
+        if need_grad:
+            ctx.save_for_backward(*saved)
         ctx.set_materialize_grads(False)
         ctx.rb, ctx.precision, ctx.has_bias = rb, precision, bias is not None
         ctx.cfg = (bool(training), bool(relu), residual is not None, bool(want_bf16))
@@ -839,13 +976,59 @@ class _ConvBNAct(torch.autograd.Function):
     def backward(ctx, da, _dab=None):
         if da is None:
             return (None,) * 16
-        x, weight, xb, y, a, gamma, mean, rstd = ctx.saved_tensors
         training, relu, has_res, want_bf16 = ctx.cfg
-        dy, dyb, dres, dgamma, dbeta = _bn_backward_impl(da, y, a, gamma, mean, rstd, training, relu, has_res,
-                                                         want_bf16 and ctx.precision == CONV_BF16)
-        dx, dw, db = _conv_backward_impl(dy, dyb, x, weight, xb, ctx.rb, ctx.precision, ctx.needs_input_grad[0],
-                                         ctx.needs_input_grad[2], ctx.has_bias and ctx.needs_input_grad[3])
+        dx, dw, db, dgamma, dbeta, dres = _layer_backward(da, ctx.saved_tensors, ctx.rb, ctx.precision, training, relu, has_res,
+                                                          ctx.has_bias and ctx.needs_input_grad[3], ctx.needs_input_grad[0],
+                                                          ctx.needs_input_grad[2])
         return dx, None, dw, db, None, None, dgamma, dbeta, None, None, None, None, None, dres, None, None
+
+
+class _ResBlock(torch.autograd.Function):
+    """SparseBasicBlock (spconv_backbone.py L30-66) as one autograd node: conv1-bn1-relu, conv2-bn2, + identity, relu.
+    Backward: layer 2, then layer 1 with the residual-branch gradient added in its dgrad epilogue (no separate add pass,
+    no autograd accumulation of the two branches)."""
+
+    @staticmethod
+    def forward(ctx, x, x_bf16, w1, b1, g1, be1, rm1, rv1, w2, b2, g2, be2, rm2, rv2, rb, precision, eps, momentum, training, want_bf16):
+        need_grad = any(ctx.needs_input_grad)
+        h, hb, s1 = _layer_forward(x, x_bf16, w1, b1, rb, precision, g1, be1, rm1, rv1, eps, momentum, training, None, True,
+                                   want_bf16, need_grad)
+        out, outb, s2 = _layer_forward(h, hb, w2, b2, rb, precision, g2, be2, rm2, rv2, eps, momentum, training, s1[0], True,
+                                       want_bf16, need_grad)
+        if need_grad:
+            ctx.save_for_backward(*s1, *s2)
+        ctx.set_materialize_grads(False)
+        ctx.rb, ctx.precision, ctx.training = rb, precision, bool(training)
+        ctx.has_bias = (b1 is not None, b2 is not None)
+        if outb is not None:
+            ctx.mark_non_differentiable(outb)
+        return out, outb
+
+    @staticmethod
+    def backward(ctx, dout, _db=None):
+        if dout is None:
+            return (None,) * 20
+        sv = ctx.saved_tensors
+        s1, s2 = sv[:8], sv[8:]
+        ng = ctx.needs_input_grad
+        dh, dw2, db2, dg2, dbe2, dres = _layer_backward(dout, s2, ctx.rb, ctx.precision, ctx.training, True, True,
+                                                        ctx.has_bias[1] and ng[9], True, ng[8])
+        dx, dw1, db1, dg1, dbe1, _ = _layer_backward(dh, s1, ctx.rb, ctx.precision, ctx.training, True, False,
+                                                     ctx.has_bias[0] and ng[3], ng[0], ng[2], addend=dres if ng[0] else None)
+        return (dx, None, dw1, db1, dg1, dbe1, None, None, dw2, db2, dg2, dbe2, None, None, None, None, None, None, None, None)
+
+
+def res_block(x, x_bf16, conv1_w, conv1_b, bn1, conv2_w, conv2_b, bn2, rb, precision, want_bf16=False):
+    """SparseBasicBlock on feature rows; bn1 / bn2 are the nn.BatchNorm1d modules.  -> (out, out_bf16 or None)"""
+    training = bn1.training or bn1.running_mean is None
+    if training:
+        for bn in (bn1, bn2):
+            if bn.running_mean is not None and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+    assert bn1.eps == bn2.eps and bn1.momentum == bn2.momentum
+    return _ResBlock.apply(x, x_bf16, conv1_w, conv1_b, bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var, conv2_w, conv2_b,
+                           bn2.weight, bn2.bias, bn2.running_mean, bn2.running_var, rb, precision, bn1.eps, bn1.momentum, training,
+                           want_bf16)
 
 
 def conv_bn_act(x, weight, bias, rb, precision, bn: torch.nn.BatchNorm1d, residual=None, relu=True, x_bf16=None, want_bf16=False):

@@ -12,7 +12,7 @@ from .. import ops
 from ..spconv_compat import pytorch as _sp
 from .backbones import make_backbones
 
-_classes = make_backbones(_sp, _sp.bn_act_tensor, _sp.conv_bn_act_tensor)
+_classes = make_backbones(_sp, _sp.bn_act_tensor, _sp.conv_bn_act_tensor, _sp.res_block_tensor)
 VoxelBackBone8x = _classes["VoxelBackBone8x"]
 VoxelResBackBone8x = _classes["VoxelResBackBone8x"]
 SparseBasicBlock = _classes["SparseBasicBlock"]

@@ -37,7 +37,7 @@ STAGES_RES = dict(
 )
 
 
-def make_backbones(sp, bn_act, conv_bn_act=None):
+def make_backbones(sp, bn_act, conv_bn_act=None, res_block=None):
     """sp: module with SparseConvTensor, SparseModule, SparseSequential, SubMConv3d, SparseConv3d.
     bn_act(sparse_tensor, bn_module, residual_features, relu) -> sparse_tensor with the new features.
     conv_bn_act(sparse_tensor, conv_module, bn_module, residual_features, relu) (optional): the same result as
@@ -70,6 +70,8 @@ def make_backbones(sp, bn_act, conv_bn_act=None):
         def forward(self, x):
             if hasattr(x, "canonical"):
                 x = x.canonical()      # the residual rows must line up with the conv outputs
+            if res_block is not None and self.conv1.indice_key is not None and self.conv1.indice_key == self.conv2.indice_key:
+                return res_block(x, self.conv1, self.bn1, self.conv2, self.bn2)     # the whole block as one autograd node
             out = conv_bn_act(x, self.conv1, self.bn1, None, True)
             return conv_bn_act(out, self.conv2, self.bn2, x.features, True)
 

@@ -116,6 +116,19 @@ def conv_bn_act_tensor(x, conv, bn, residual, relu):
                             index_out, ab)
 
 
+def res_block_tensor(x, conv1, bn1, conv2, bn2):
+    """SparseBasicBlock (two SubMConv3d sharing one rulebook, BN, residual, ReLU) as one autograd node (ops.res_block)."""
+    x = x.canonical()
+    rb, index_out = conv1._rulebook(x)
+    rb2, _ = conv2._rulebook(x)
+    assert rb2 is rb, "SparseBasicBlock: both convolutions must share one indice_key"
+    bf16 = _precision == ops.CONV_BF16
+    a, ab = ops.res_block(x.features, x._features_bf16, conv1.weight, conv1.bias, bn1, conv2.weight, conv2.bias, bn2, rb,
+                          _precision, bf16)
+    return SparseConvTensor(a, rb.out_coords, rb.out_shape, x.batch_size, x.grid, x.voxel_num, x.indice_dict, x.benchmark,
+                            index_out, ab)
+
+
 class SparseModule(nn.Module):
     """Marker base: SparseSequential hands the whole SparseConvTensor to these."""
     pass
