@@ -36,6 +36,8 @@ extern "C" {
 
 const char *toda_last_error(void);
 int toda_version(void);
+/* number of kernels this library has launched in the calling process (bench.py reports the per-run delta as gpu_launches) */
+long long toda_launch_count(void);
 /* number of SMs / compute capability of the current device; fails when there is no CUDA device. */
 int toda_device_info(int *sm_count_host, int *cc_major_host, int *cc_minor_host);
 

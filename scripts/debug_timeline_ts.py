@@ -45,6 +45,9 @@ print("tile starts (g):", tiles_g[:16])
 print("-- MMA warp per tile: start, +wait acc_empty")
 for it in range(3, 12):
     print("tile %2d  start %8d  acc_empty wait %5d" % (it, int(t[14, it] - t0), int(t[15, it] - t[14, it])))
+print("-- gather warp 8 per tile: loop top, +lidx wait | pairs done, +release all")
+for it in range(3, 12):
+    print("tile %2d  top %8d +%5d | pairs done %8d +%5d" % (it, int(t[22, it] - t0), int(t[23, it] - t[22, it]), int(t[20, it] - t0), int(t[21, it] - t[20, it])))
 print("-- per pair (first g of the pair): gather: start, +release/slabwait, +loads issued & a_empty ok, +fix/sync, +sttm..arrive | MMA: start, +waits, +issue")
 g_lo, g_hi = int(tiles_g[4]), int(tiles_g[9])
 for g in range(g_lo, min(g_hi, 255)):

@@ -16,6 +16,7 @@ _FP = ctypes.POINTER(ctypes.c_float)
 SIGNATURES = {
     "toda_last_error": (ctypes.c_char_p, []),
     "toda_version": (c_int, []),
+    "toda_launch_count": (ctypes.c_longlong, []),
     "toda_device_info": (c_int, [_IP, _IP, _IP]),
     "toda_index_bytes": (c_sz, [c_int] * 4),
     "toda_index_insert": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]),

@@ -29,7 +29,9 @@ void toda_set_error(const char *fmt, ...);
         }                                                                                     \
     } while (0)
 
-#define TODA_LAUNCH_OK() TODA_CUDA_OK(cudaGetLastError())
+// every kernel launch of the library passes here: the count behind toda_launch_count() (bench.py's gpu_launches)
+extern long long g_toda_launches;
+#define TODA_LAUNCH_OK() do { ++g_toda_launches; TODA_CUDA_OK(cudaGetLastError()); } while (0)
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 

@@ -35,9 +35,12 @@ constexpr int kGatherWarps = 16;                  // four warpgroups; a lone war
 constexpr int kWarpMma = 4, kWarpLoader = 5, kWarpB = 6, kWarpLoader2 = 7, kWarpGather0 = 8;
 constexpr int kThreads = 24 * 32;
 // A ring: pair slots of 2 x 32 TMEM columns (2 x 64 K elements) behind the two accumulators
-// Four slots = one per gather warpgroup: pair gp is produced by warpgroup gp % 4 into slot gp % 4, so every waiter of a slot's
-// barriers sees each of its phases in turn (a parity wait by a thread that is two phases behind would pass at once).
-template <int COUT> struct ARing { static constexpr int kSlots = 4; static constexpr int kCol0 = 256; };
+// Pair gp is produced by warpgroup gp % 4 into slot gp % kSlots.  Its barriers are NOT per slot but per pair index modulo
+// 16 (a_full / a_empty[gp & 15]): every barrier is then waited on by one warpgroup only, which sees each of its phases in turn
+// -- a parity wait by a thread that is two phases behind would pass at once (this hung the kernel when barriers were per slot
+// and a warpgroup without work in a few sparse tiles ran ahead).
+template <int COUT> struct ARing { static constexpr int kSlots = COUT <= 64 ? 6 : 4; static constexpr int kCol0 = COUT <= 64 ? 128 : 256; };
+constexpr int kABars = 16;
 constexpr int kPlanWindow = 32768;                // block-id window of the plan kernel's bitmap
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -146,7 +149,7 @@ template <int CIN, int COUT> struct TsCfg {
     static constexpr int kSB = kBRes ? kNkbMax : (COUT == 128 ? 4 : (COUT == 64 ? 6 : 8));
     static constexpr int kParts = CIN >= 64 ? 1 : 64 / CIN;    // kernel offsets per 64-element K block
     static constexpr int kPV = (CIN >= 64 ? 64 : CIN) / 8;     // 16-byte vectors per part
-    static constexpr int kSmemRaw = 1024 + kSB * kBStage + kNB * kSlab + 2 * kLidxBytes + 512 + 256;
+    static constexpr int kSmemRaw = 1024 + kSB * kBStage + kNB * kSlab + 2 * kLidxBytes + 640 + 256;
     // the kernel allocates all 512 TMEM columns: never let two CTAs share an SM (the second would wait in tcgen05.alloc)
     static constexpr int kSmem = kSmemRaw < 120 * 1024 ? 120 * 1024 : kSmemRaw;
     static_assert(kCap <= 32 && kSlab % 1024 == 0 && kBStage % 1024 == 0, "slab layout");
@@ -191,13 +194,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
     const uint32_t slab_base = base + SB * C::kBStage;
     const uint32_t lidx_base = slab_base + NB * C::kSlab;
     const uint32_t bar_base = lidx_base + 2 * kLidxBytes;
-    const uint32_t a_full = bar_base, a_empty = bar_base + 64;               // 8 + 8
-    const uint32_t b_full = bar_base + 128, b_empty = bar_base + 240;         // 14 + 14
-    const uint32_t acc_full = bar_base + 352, acc_empty = bar_base + 368;     // 2 + 2
-    const uint32_t slab_full = bar_base + 384, slab_empty = bar_base + 408;   // 3 + 3
-    const uint32_t lidx_full = bar_base + 432, lidx_empty = bar_base + 448;   // 2 + 2
-    const uint32_t tmem_slot = bar_base + 464;
-    const uint32_t zero_base = bar_base + 512;               // 256 zero bytes: the row read for a missing neighbour
+    const uint32_t a_full = bar_base, a_empty = bar_base + 128;              // 16 + 16
+    const uint32_t b_full = bar_base + 256, b_empty = bar_base + 368;         // 14 + 14
+    const uint32_t acc_full = bar_base + 480, acc_empty = bar_base + 496;     // 2 + 2
+    const uint32_t slab_full = bar_base + 512, slab_empty = bar_base + 536;   // 3 + 3
+    const uint32_t lidx_full = bar_base + 560, lidx_empty = bar_base + 576;   // 2 + 2
+    const uint32_t tmem_slot = bar_base + 592;
+    const uint32_t zero_base = bar_base + 640;               // 256 zero bytes: the row read for a missing neighbour
     volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *)(smem_raw + (tmem_slot - raw));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -207,22 +210,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
     // A tile without any neighbour still walks block 0 (all-zero rows) so that its accumulator is defined.
     // (the offset mask of the NEXT tile is fetched while the current tile is processed: load_om / kb_mask_from)
     auto load_om = [&](int t) -> uint32_t { return (tile_masks && t < num_tiles) ? __ldg(tile_masks + t) : 0xffffffffu; };
+    // (warp-collective: lane c tests K block c (and c + 32), two ballots give the mask -- the 14..54-iteration scalar loop this
+    // replaces sat on every role's critical path at each tile start)
     auto kb_mask_from = [&](uint32_t om) -> unsigned long long {
         if (!tile_masks) return nkb >= 64 ? ~0ull : ((1ull << nkb) - 1ull);
-        unsigned long long cm = 0ull;
+        const int c0 = lane, c1 = lane + 32;
+        bool b0, b1;
         if (CIN <= 64) {
-            for (int c = 0; c < nkb; ++c)
-                if ((om >> (c * PARTS)) & ((1u << PARTS) - 1u)) cm |= 1ull << c;
+            b0 = c0 < nkb && ((om >> (c0 * PARTS)) & ((1u << PARTS) - 1u)) != 0u;
+            b1 = false;
         } else {
-            for (int c = 0; c < nkb; ++c)
-                if ((om >> (c >> 1)) & 1u) cm |= 1ull << c;
+            b0 = c0 < nkb && ((om >> (c0 >> 1)) & 1u) != 0u;
+            b1 = c1 < nkb && ((om >> (c1 >> 1)) & 1u) != 0u;
         }
+        const unsigned lo = __ballot_sync(0xffffffffu, b0);
+        const unsigned hi = CIN <= 64 ? 0u : __ballot_sync(0xffffffffu, b1);
+        const unsigned long long cm = (unsigned long long)lo | ((unsigned long long)hi << 32);
         return cm ? cm : 1ull;
     };
     auto kb_mask_of = [&](int t) -> unsigned long long { return kb_mask_from(load_om(t)); };
 
     if (tid == 0) {
-        for (int s = 0; s < kASlots; ++s) {
+        for (int s = 0; s < kABars; ++s) {
             mbar_init(a_full + 8 * s, 4);          // the four warps of the gathering warpgroup
             mbar_init(a_empty + 8 * s, 1);         // tcgen05.commit
         }
@@ -273,7 +282,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
             const int ib = it & 1;
             const uint32_t om = om_next;
             om_next = load_om(t + gridDim.x);
+            TS_DBG(tid == 256, 22, it);
             if (!(xmode & 64)) mbar_wait(lidx_full + 8 * ib, (it >> 1) & 1);
+            TS_DBG(tid == 256, 23, it);
             const uint32_t lidx_tile = lidx_base + ib * kLidxBytes + 2 * row;
             const int unit0 = it * ngroups;             // (tile, group) units are numbered consecutively per CTA
             int gwait = 0, gdone = 0;                   // groups of this tile whose slab this warp has waited for / released
@@ -373,8 +384,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
                 // for only after the first block's loads are in flight: the barrier probe overlaps them)
                 uint32_t va[32];
                 bool fix = load_block(kbA, va);
-                if (gp >= kASlots) {
-                    mbar_wait(a_empty + 8 * aslot, ((gp / kASlots) - 1) & 1);
+                if (gp >= kASlots) {         // the pair that used this slot before (gp - kASlots) has been consumed
+                    mbar_wait(a_empty + 8 * ((gp - kASlots) & (kABars - 1)), ((gp - kASlots) / kABars) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 TS_DBG((tid & 127) == 0, 12, gA);
@@ -391,13 +402,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(a_full + 8 * aslot);
+                if (lane == 0) mbar_arrive(a_full + 8 * (gp & (kABars - 1)));
                 TS_DBG((tid & 127) == 0, 3, gA);
                 TS_DBG(lane == 0, 16 + (warp - kWarpGather0), gA);
             }
             gbase += nact;
             gpbase += (nact + 1) >> 1;
+            TS_DBG(tid == 256, 20, it);
             release_below(ngroups);
+            TS_DBG(tid == 256, 21, it);
             __syncwarp();
             if (lane == 0 && !(xmode & 64)) mbar_arrive(lidx_empty + 8 * ib);
         }
@@ -497,7 +510,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
                 const int n = kbB >= 0 ? 2 : 1;
                 j += 2;
                 const int aslot = gp % kASlots;
-                mbar_wait(a_full + 8 * aslot, (gp / kASlots) & 1);
+                mbar_wait(a_full + 8 * (gp & (kABars - 1)), (gp / kABars) & 1);
                 if (!BRES) {
                     mbar_wait(b_full + 8 * (gA % SB), (gA / SB) & 1);
                     if (n == 2) mbar_wait(b_full + 8 * ((gA + 1) % SB), ((gA + 1) / SB) & 1);
@@ -521,7 +534,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
                             if (!BRES) umma_commit(b_empty + 8 * stage);
                         }
                     }
-                    umma_commit(a_empty + 8 * aslot);
+                    umma_commit(a_empty + 8 * (gp & (kABars - 1)));
                 }
                 accumulate = 1u;
                 __syncwarp();
@@ -579,24 +592,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
             }
         }
     } else {
-        // ------------------------------------------------------------------ weight producer
-        if (lane == 0) {
-            if (BRES) {
+        // ------------------------------------------------------------------ weight producer (the warp walks the tiles together: the
+        // K-block mask is a warp-collective; lane 0 issues the TMA copies)
+        if (BRES) {
+            if (lane == 0) {
                 // every K block once, resident for the lifetime of the CTA
                 mbar_arrive_expect_tx(b_full, (uint32_t)nkb * C::kBStage);
                 for (int kb = 0; kb < nkb; ++kb) tma_load_2d(base + kb * C::kBStage, &map_w, kb * 64, 0, b_full);
-            } else {
-                int g = 0;
-                for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                    for (unsigned long long cm = kb_mask_of(t); cm; cm &= cm - 1, ++g) {
+            }
+        } else {
+            int g = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const unsigned long long cm0 = kb_mask_of(t);
+                if (lane == 0) {
+                    int gg = g;
+                    for (unsigned long long cm = cm0; cm; cm &= cm - 1, ++gg) {
                         const int kb = __ffsll((long long)cm) - 1;
-                        const int stage = g % SB, use = g / SB;
+                        const int stage = gg % SB, use = gg / SB;
                         if (use > 0) mbar_wait(b_empty + 8 * stage, (use - 1) & 1);
-                        TS_DBG(true, 13, g);
+                        TS_DBG(true, 13, gg);
                         mbar_arrive_expect_tx(b_full + 8 * stage, C::kBStage);
                         tma_load_2d(base + stage * C::kBStage, &map_w, kb * 64, 0, b_full + 8 * stage);
                     }
                 }
+                g += __popcll(cm0);
+                __syncwarp();
             }
         }
     }

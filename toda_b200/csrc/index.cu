@@ -15,6 +15,8 @@ void toda_set_error(const char *fmt, ...) {
 }
 
 extern "C" const char *toda_last_error(void) { return g_err; }
+long long g_toda_launches = 0;
+extern "C" long long toda_launch_count(void) { return g_toda_launches; }
 extern "C" int toda_version(void) { return 100; }
 
 extern "C" int toda_device_info(int *sm_count, int *cc_major, int *cc_minor) {

@@ -17,22 +17,22 @@ ORDER_CANONICAL = 1
 CONV_FP32 = 0
 CONV_BF16 = 1
 
-# launches of this library's kernels since the last reset (bench.py reports it as gpu_launches)
-_launches = 0
+# launches of this library's kernels since the last reset (bench.py reports it as gpu_launches): counted inside the
+# library, at every launch site (toda_launch_count)
+_launch_base = 0
 
 
 def launches():
-    return _launches
+    return int(_C.lib().toda_launch_count()) - _launch_base
 
 
 def reset_launches():
-    global _launches
-    _launches = 0
+    global _launch_base
+    _launch_base = int(_C.lib().toda_launch_count())
 
 
 def _count(n):
-    global _launches
-    _launches += n
+    pass
 
 
 # optional per-call device timing (bench.py's roofline pass): list of (name, meta, start_event, end_event)
