@@ -278,6 +278,8 @@ def run_ours(args, rank, world, local_rank):
     # a DataLoader's prefetch would.
     pipe = InputPipeline(vfe, net, device)
 
+    host = dict(front=0.0, back=0.0)     # host wall time inside the two halves of a step (front includes its small device waits)
+
     def front(points, offsets, pending):
         t0 = time.perf_counter()
         if trace is not None:
@@ -285,6 +287,7 @@ def run_ours(args, rank, world, local_rank):
             faulthandler.dump_traceback_later(0.012, file=sys.stderr)     # where is the host if a front stalls?
         h = pipe.submit({"points": points, "point_frame_offsets": offsets, "batch_size": FRAMES_PER_GPU},
                         inputs_pending=pending)
+        host["front"] += time.perf_counter() - t0
         if trace is not None:
             faulthandler.cancel_dump_traceback_later()
             trace.append(("front", round((time.perf_counter() - t0) * 1e3, 2)))
@@ -301,6 +304,7 @@ def run_ours(args, rank, world, local_rank):
             loss.backward()
             if reduce:
                 bucket.all_reduce_mean()
+        host["back"] += time.perf_counter() - t0
         if trace is not None:
             trace.append(("back", round((t1 - t0) * 1e3, 2), round((time.perf_counter() - t1) * 1e3, 2)))
         return loss, bd
@@ -326,6 +330,7 @@ def run_ours(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     mark0 = len(trace) if trace is not None else 0
+    host["front"] = host["back"] = 0.0
     e0.record()
     marks[0].record()
     for i in range(args.steps):
@@ -343,6 +348,7 @@ def run_ours(args, rank, world, local_rank):
             print("host trace (ms) of the timed steps: " + " ".join(str(t) for t in trace[mark0:]), file=sys.stderr)
     ms = e0.elapsed_time(e1)
     launches = ops.launches()
+    host_ms = dict(fwd_bwd=host["back"] * 1e3 / args.steps, front=host["front"] * 1e3 / args.steps)
     t = torch.tensor([ms], device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -400,7 +406,10 @@ def run_ours(args, rank, world, local_rank):
                             voxels_per_frame=int(bd["voxel_coords"].shape[0] / FRAMES_PER_GPU), conv_precision=args.precision,
                             l2="inputs rotate over %d pre-staged batches and each step streams >1 GB of activations (>> 126 MB L2)" % POOL,
                             parallelism=f"dp{world} (frame-sharded" + (", bucketed grad all-reduce overlapped with backward)" if train else ", no collective: forward only)")),
-                clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roof, roofline_layers=layers)
+                clocks=clocks, e2e=e2e, gpu_launches=int(launches), launches_per_step=launches / args.steps,
+                host_ms_per_step=round(host_ms["fwd_bwd"] + host_ms["front"], 3),
+                host_ms_detail=dict(fwd_bwd=round(host_ms["fwd_bwd"], 3), front_incl_device_waits=round(host_ms["front"], 3)),
+                roofline=roof, roofline_layers=layers)
     return line
 
 

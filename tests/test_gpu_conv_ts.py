@@ -39,7 +39,7 @@ def test_plan_kernel_matches_round1_kernel_subm(n, cin, cout):
     try:
         rb = ops.rulebook_subm(index, [3, 3, 3], channels=max(cin, cout))
     finally:
-        ops.set_tile_plans(False)
+        ops.set_tile_plans(True)
     assert rb.plan is not None
     x = torch.from_numpy(feats).to(DEV)
     w = torch.randn(27, cin, cout, device=DEV) * 0.1
@@ -89,7 +89,7 @@ def test_plan_kernel_full_size_chain_all_geometries():
                 (ya, _), (yb, _) = _both(dy, cout, rb.nbr_bwd, rb.n_in, kvol, wt, cin, rb.dgrad_plan, None)
             assert torch.equal(ya, yb), ("down dgrad", cin, cout)
     finally:
-        ops.set_tile_plans(False)
+        ops.set_tile_plans(True)
 
 
 def test_backbone_step_with_plans_is_bit_identical():
@@ -110,7 +110,7 @@ def test_backbone_step_with_plans_is_bit_identical():
             _, net = PU.build_pair("VoxelResBackBone8x", 5, g["grid_size"], seed=int(g["seed"]))
             res.append(PU.run_backbone(net, hc, vf, vc, 2, cot=cot, train=True))
     finally:
-        ops.set_tile_plans(False)
+        ops.set_tile_plans(True)
         G.set_conv_precision("fp32")
     a, b = res
     assert np.array_equal(a["spatial_features"], b["spatial_features"])

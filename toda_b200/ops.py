@@ -489,11 +489,11 @@ def rulebook_sparse(index_in: OccupancyIndex, ksize, stride, padding, tag, cin=N
     return rb, index_out
 
 
-# Row-cache plans (toda_table_tile_plan) + the TMEM-operand kernel of conv_ts.cu.  Off by default: on the bench batch the
-# kernel is ~7 % faster than the cp.async / gather4 kernels over forward + dgrad, but building nine plans per batch costs the
-# (host-bound) step more than that (profiles/r02_conv_ts.md).  TODA_TILE_PLANS=1 or set_tile_plans(True) enables it.
+# Row-cache plans (toda_table_tile_plan) + the TMEM-operand kernel of conv_ts.cu: 14-22 % faster per layer than the round-1
+# cp.async / gather4 kernels over forward + dgrad (profiles/r02_conv_ts.md); the nine plans per batch are built with the
+# rulebooks on the input pipeline's side stream.  TODA_TILE_PLANS=0 or set_tile_plans(False) keeps the round-1 kernels.
 import os as _os
-_TILE_PLANS = _os.environ.get("TODA_TILE_PLANS", "0") != "0"
+_TILE_PLANS = _os.environ.get("TODA_TILE_PLANS", "1") != "0"
 
 
 def set_tile_plans(on):
