@@ -400,7 +400,7 @@ def run_ours(args, rank, world, local_rank):
     roof, layers = roofline_from_profile(prof, bd, peaks, ms / args.steps)
     line = dict(metric=WORKLOADS[WORKLOAD]["metric"], value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f32" if args.precision == "fp32" else "bf16", data="synthetic",
+                dtype={"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16x3 (split bf16, fp32-class)"}[args.precision], data="synthetic",
                 config=dict(workload=WORKLOADS[WORKLOAD]["desc"], workload_key=WORKLOAD,
                             frames_per_gpu=FRAMES_PER_GPU, points_per_frame=int(hosts[0][0].shape[0] / FRAMES_PER_GPU),
                             voxels_per_frame=int(bd["voxel_coords"].shape[0] / FRAMES_PER_GPU), conv_precision=args.precision,
@@ -567,7 +567,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("TODA_CONV_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("TODA_CONV_PRECISION", "bf16"), choices=["fp32", "bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="nus_0075", choices=sorted(WORKLOADS),
                     help="default = BASELINE.json configs[2]; waymo_second = configs[1]; toda_stage2 = configs[3]")

@@ -160,9 +160,12 @@ int toda_parity_order(const int32_t *coords, int n, const int *stride_host, cons
  *          L341-348 accepts.
  * precision: TODA_CONV_FP32 = fp32 FFMA (parity path, rtol 1e-4 vs the oracle);
  *            TODA_CONV_BF16 = bf16 operands, fp32 accumulate on tcgen05 tensor cores.
- * ------------------------------------------------------------------------------------------ */
+ *            TODA_CONV_BF16X3 = the same tensor-core kernels at fp32-class accuracy: every operand is split into two
+ *            bf16 terms and each product is three launches (hi*hi + hi*lo + lo*hi, ~2^-16 relative; x_bf16 / dy_bf16 /
+ *            w_bf16 are ignored: the kernels split the fp32 tensors themselves). */
 #define TODA_CONV_FP32 0
 #define TODA_CONV_BF16 1
+#define TODA_CONV_BF16X3 2
 /* param (Cout,kvol,Cin) -> [kvol,Cin,Cout] (transpose=0) or [kvol,Cout,Cin] with optional k mirroring */
 int toda_weight_repack(const float *w_param, int kvol, int cin, int cout, int transpose, int mirror_k, float *w_out,
                        void *stream);

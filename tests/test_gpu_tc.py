@@ -242,3 +242,67 @@ def test_tc_matches_ffma_path_at_scale(cin, cout, n):
     index.release()
     for name, a, b in zip(("fwd", "dgrad", "wgrad"), out[ops.CONV_BF16], out[ops.CONV_FP32]):
         PU.assert_close(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-3, atol_scale=1e-4, what=f"{name} {cin}->{cout} n={n}")
+
+
+# ------------------------------------------------------------------------------------------ bf16x3: fp32-class accuracy on tensor cores
+@pytest.mark.parametrize("subm,cin,cout,k,s,p", [
+    (True, 5, 16, 3, 1, 1), (True, 4, 16, 3, 1, 1), (True, 16, 16, 3, 1, 1), (True, 32, 32, 3, 1, 1), (True, 64, 64, 3, 1, 1), (True, 128, 128, 3, 1, 1),
+    (False, 16, 32, 3, 2, 1), (False, 64, 128, 3, 2, (0, 1, 1)), (False, 128, 128, (3, 1, 1), (2, 1, 1), 0)])
+def test_x3_conv_matches_fp32_oracle_at_rtol_1e4(subm, cin, cout, k, s, p):
+    """TODA_CONV_BF16X3 (split-bf16, three tcgen05 launches per product) against the fp32 oracle on UNROUNDED operands:
+    forward, dgrad, wgrad and bias gradient within the north star's fp32 tolerance (rtol 1e-4)."""
+    from oracle import spconv_oracle as S
+    from toda_b200.spconv_compat import pytorch as G
+    torch.manual_seed(0)
+    mk = (lambda sp: sp.SubMConv3d(cin, cout, k, padding=p, bias=True, indice_key="a")) if subm else \
+        (lambda sp: sp.SparseConv3d(cin, cout, k, stride=s, padding=p, bias=True, indice_key="a"))
+    a, b = mk(S), mk(G)
+    b.load_state_dict(a.state_dict())
+    b = b.to(DEV)
+    shape, n, batch = [9, 24, 31], 3000, 2
+    feats, idx = PU.random_sparse(7, batch, shape, n, cin)
+    fa = torch.from_numpy(feats).requires_grad_(True)
+    fb = torch.from_numpy(feats).to(DEV).requires_grad_(True)
+    ya = a(S.SparseConvTensor(fa, torch.from_numpy(idx), shape, batch))
+    G.set_conv_precision("bf16x3")
+    try:
+        yb = b(G.SparseConvTensor(fb, torch.from_numpy(idx).to(DEV), shape, batch))
+        assert np.array_equal(yb.indices.cpu().numpy(), ya.indices.numpy())
+        PU.assert_close(yb.features.detach().cpu().numpy(), ya.features.detach().numpy(), what="x3 fwd")
+        g = torch.randn(ya.features.shape, generator=torch.Generator().manual_seed(3))
+        ya.features.backward(g)
+        yb.features.backward(g.to(DEV))
+    finally:
+        G.set_conv_precision("fp32")
+    PU.assert_close(fb.grad.cpu().numpy(), fa.grad.numpy(), what="x3 dgrad")
+    PU.assert_close(b.weight.grad.cpu().numpy(), a.weight.grad.numpy(), what="x3 wgrad")
+    PU.assert_close(b.bias.grad.cpu().numpy(), a.bias.grad.numpy(), what="x3 bias grad")
+
+
+def test_backbone_x3_vs_reference_golden():
+    """VoxelResBackBone8x fwd+bwd in bf16x3 mode against the golden produced through the reference's own spconv_backbone.py.
+    Every single convolution meets rtol 1e-4 (test above); through 21 layers with batch-statistics BatchNorm the ~1e-5
+    per-layer error compounds to ~1e-4, so the end-to-end tolerance stated for this mode is rtol 5e-4 on activations and
+    3e-3 on gradients (the bf16 mode's is 5e-2 / 3e-2, the FFMA path's 1e-4 / 1e-3)."""
+    import toda_b200.pcdet_plugin as P
+    from toda_b200.spconv_compat import pytorch as G
+    g = PU.load_golden("backbone_res.npz")
+    twin, net = PU.build_pair("VoxelResBackBone8x", 5, g["grid_size"], seed=int(g["seed"]))
+    hc = P.HeightCompression(PU.Cfg(NUM_BEV_FEATURES=256))
+    vf = torch.from_numpy(g["voxel_features"]).to(DEV)
+    vc = torch.from_numpy(g["voxel_coords"]).float().to(DEV)
+    cot = torch.randn(tuple(g["bev_shape"]), generator=torch.Generator().manual_seed(int(g["seed"])))
+    G.set_conv_precision("bf16x3")
+    try:
+        r = PU.run_backbone(net, hc, vf, vc, 2, cot=cot, train=True)
+    finally:
+        G.set_conv_precision("fp32")
+    f_sorted, i_sorted = PU.sort_rows(r["enc_features"], r["enc_indices"])
+    assert np.array_equal(i_sorted, g["train_enc_indices"])
+    PU.assert_close(f_sorted, g["train_enc_features"], rtol=5e-4, atol_scale=5e-5, what="x3 encoded features")
+    PU.assert_close(r["dvoxel_features"], g["train_dvoxel_features"], rtol=3e-3, atol_scale=3e-4, what="x3 d voxel_features")
+    names = [str(n) for n in g["grad_names"]]
+    norms = np.array([np.linalg.norm(r["grads"][n].astype(np.float64)) for n in names])
+    np.testing.assert_allclose(norms, g["grad_norms"], rtol=3e-3, atol=1e-6 * float(g["grad_norms"].max()))
+    PU.assert_close(r["grads"]["conv_out.0.weight"], g["grad_conv_out_weight"], rtol=3e-3, atol_scale=3e-4, what="x3 wgrad out")
+    PU.assert_close(r["grads"]["conv_input.0.weight"], g["grad_conv_input_weight"], rtol=3e-3, atol_scale=3e-4, what="x3 wgrad in")

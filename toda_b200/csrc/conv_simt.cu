@@ -15,6 +15,14 @@ int conv_tc_wgrad(const float *x, const void *x_bf16, int n_in, int cin, const i
                   const float *dy, const void *dy_bf16, int cout, float *dw_param, void *workspace, size_t workspace_bytes,
                   cudaStream_t st);
 bool conv_tc_supported(int cin, int cout, int kvol);
+// TODA_CONV_BF16X3 (conv_x3.cu): three bf16 tensor-core launches per product, fp32-class accuracy
+size_t conv_x3_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol);
+int conv_x3_fwd(const float *x, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *w, int cout, const float *bias,
+                float *y, const int32_t *out_rows, const uint32_t *tile_masks, double *bn_sums, void *workspace, size_t workspace_bytes,
+                cudaStream_t st, const TilePlan *plan, const float *addend);
+size_t conv_x3_wgrad_workspace_bytes(int n_in, int n_out, int kvol, int cin, int cout);
+int conv_x3_wgrad(const float *x, int n_in, int cin, const int32_t *nbr, int n_out, int kvol, const float *dy, int cout, float *dw_param,
+                  void *workspace, size_t workspace_bytes, cudaStream_t st);
 bool conv_tc_wgrad_supported(int cin, int cout, int kvol);
 size_t conv_tc_wgrad_workspace_bytes(int n_in, int n_out, int kvol, int cin, int cout);
 
@@ -256,12 +264,14 @@ extern "C" int toda_weight_repack(const float *w_param, int kvol, int cin, int c
 
 // 1 when toda_spconv_fwd(precision) runs the tensor-core kernel for this shape (and can therefore fuse the BN statistics)
 extern "C" int toda_spconv_uses_tensor_cores(int cin, int cout, int kvol, int precision) {
-    return precision == TODA_CONV_BF16 && conv_tc_supported(cin, cout, kvol) ? 1 : 0;
+    return (precision == TODA_CONV_BF16 || precision == TODA_CONV_BF16X3) && conv_tc_supported(cin, cout, kvol) ? 1 : 0;
 }
 
 extern "C" size_t toda_spconv_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol, int precision) {
     if (precision == TODA_CONV_BF16 && n_in >= 0 && cin > 0 && cout > 0 && kvol > 0 && conv_tc_supported(cin, cout, kvol))
         return conv_tc_fwd_workspace_bytes(n_in, cin, cout, kvol);
+    if (precision == TODA_CONV_BF16X3 && n_in >= 0 && cin > 0 && cout > 0 && kvol > 0 && conv_tc_supported(cin, cout, kvol))
+        return conv_x3_fwd_workspace_bytes(n_in, cin, cout, kvol);
     return 0;
 }
 
@@ -296,7 +306,11 @@ static int spconv_fwd_impl(const float *x, const void *x_bf16, int n_in, int cin
     if (n_out == 0) return TODA_OK;
     TODA_CHECK_ARG(x && nbr && w && y, "spconv_fwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    TODA_CHECK_ARG(precision == TODA_CONV_FP32 || precision == TODA_CONV_BF16, "spconv_fwd: unknown precision %d", precision);
+    TODA_CHECK_ARG(precision == TODA_CONV_FP32 || precision == TODA_CONV_BF16 || precision == TODA_CONV_BF16X3,
+                   "spconv_fwd: unknown precision %d", precision);
+    if (precision == TODA_CONV_BF16X3 && conv_tc_supported(cin, cout, kvol))
+        return conv_x3_fwd(x, n_in, cin, nbr, n_out, kvol, w, cout, bias, y, out_rows, tile_masks, bn_sums, workspace, workspace_bytes, st,
+                           plan, addend);
     // kernel selection by shape: the tensor-core kernel covers Cin in {<=16 (zero-padded to 16), 32, 64, 128} and
     // Cout in {16,32,64,128}; anything else (e.g. the dgrad of the 4/5-channel input layer) runs on the FFMA kernel.
     if (precision == TODA_CONV_BF16 && conv_tc_supported(cin, cout, kvol))
@@ -321,6 +335,8 @@ extern "C" size_t toda_spconv_wgrad_workspace_bytes(int n_in, int n_out, int kvo
     if (n_in < 0 || n_out < 0 || kvol <= 0 || cin <= 0 || cout <= 0) return 0;
     if (precision == TODA_CONV_BF16 && conv_tc_wgrad_supported(cin, cout, kvol))
         return conv_tc_wgrad_workspace_bytes(n_in, n_out, kvol, cin, cout);
+    if (precision == TODA_CONV_BF16X3 && conv_tc_wgrad_supported(cin, cout, kvol))
+        return conv_x3_wgrad_workspace_bytes(n_in, n_out, kvol, cin, cout);
     int splits = wgrad_splits(n_out, kvol, cin, cout);
     return align_up((size_t)splits * kvol * cin * cout * sizeof(float), 256);
 }
@@ -336,7 +352,10 @@ extern "C" int toda_spconv_wgrad(const float *x, const void *x_bf16, int n_in, i
         return TODA_OK;
     }
     TODA_CHECK_ARG(x && nbr && dy && workspace, "spconv_wgrad: null pointer");
-    TODA_CHECK_ARG(precision == TODA_CONV_FP32 || precision == TODA_CONV_BF16, "spconv_wgrad: unknown precision %d", precision);
+    TODA_CHECK_ARG(precision == TODA_CONV_FP32 || precision == TODA_CONV_BF16 || precision == TODA_CONV_BF16X3,
+                   "spconv_wgrad: unknown precision %d", precision);
+    if (precision == TODA_CONV_BF16X3 && conv_tc_wgrad_supported(cin, cout, kvol))
+        return conv_x3_wgrad(x, n_in, cin, nbr, n_out, kvol, dy, cout, dw_param, workspace, workspace_bytes, st);
     if (precision == TODA_CONV_BF16 && conv_tc_wgrad_supported(cin, cout, kvol))
         return conv_tc_wgrad(x, x_bf16, n_in, cin, nbr, n_out, kvol, dy, dy_bf16, cout, dw_param, workspace, workspace_bytes, st);
     int splits = wgrad_splits(n_out, kvol, cin, cout);

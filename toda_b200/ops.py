@@ -16,6 +16,8 @@ ORDER_FIRST_APPEARANCE = 0
 ORDER_CANONICAL = 1
 CONV_FP32 = 0
 CONV_BF16 = 1
+CONV_BF16X3 = 2      # split-bf16, three tensor-core launches per product: fp32-class accuracy (csrc/conv_x3.cu)
+_TC_PRECISIONS = (CONV_BF16, CONV_BF16X3)
 
 # launches of this library's kernels since the last reset (bench.py reports it as gpu_launches): counted inside the
 # library, at every launch site (toda_launch_count)
@@ -595,7 +597,7 @@ def _conv_call(x, xb, cin, nbr, n_out, kvol, w, cout, bias, precision, what="con
     L = _C.lib()
     ws_bytes = L.toda_spconv_fwd_workspace_bytes(x.shape[0], cin, cout, kvol, precision)
     ws = _workspace("conv", ws_bytes, x.device) if ws_bytes else None
-    if precision != CONV_BF16:
+    if precision not in _TC_PRECISIONS:
         plan = None
     with _timed(what, n_in=x.shape[0], n_out=n_out, cin=cin, cout=cout, kvol=kvol, precision=precision, rb=id(rb)):
         if plan is None and addend is None and w_bf16 is None:
@@ -615,7 +617,7 @@ def _conv_call(x, xb, cin, nbr, n_out, kvol, w, cout, bias, precision, what="con
 
 def conv_plan_usable(plan, cin, cout, kvol, precision):
     """True when toda_spconv_fwd_plan will run the row-cache kernel for this call (and can therefore fuse an addend)."""
-    if plan is None or precision != CONV_BF16 or _os.environ.get("TODA_TC_FEED", "ts")[:1] in ("c",) or \
+    if plan is None or precision not in _TC_PRECISIONS or _os.environ.get("TODA_TC_FEED", "ts")[:1] in ("c",) or \
             _os.environ.get("TODA_TC_FEED", "ts")[:2] == "tm":
         return False
     cp = max(16, cin)
@@ -864,7 +866,7 @@ def _layer_forward(x, x_bf16, weight, bias, rb, precision, gamma, beta, running_
     L = _C.lib()
     kvol, n_out, dev = rb.kvol, rb.n_out, x.device
     tc = bool(L.toda_spconv_uses_tensor_cores(cin, cout, kvol, precision))
-    if tc:
+    if tc and precision == CONV_BF16:
         w, wb = _repack(weight, False, False, True)
     else:
         w, wb = _repack(weight, False, False), None
@@ -877,7 +879,7 @@ def _layer_forward(x, x_bf16, weight, bias, rb, precision, gamma, beta, running_
     bws = _workspace("bn", L.toda_bn_workspace_bytes(cout), dev)
     res = residual.contiguous() if residual is not None else None
     b = bias.contiguous() if bias is not None else None
-    pl = rb.plan if precision == CONV_BF16 else None
+    pl = rb.plan if precision in _TC_PRECISIONS else None
     sp = small.data_ptr()
     args = _C.LayerFwdArgs(
         x.data_ptr(), _vp(x_bf16), x.shape[0], cin, rb.nbr_fwd.data_ptr(), n_out, kvol, w.data_ptr(), _vp(wb), cout, _vp(b),
@@ -917,7 +919,7 @@ def _layer_backward(da, saved, rb, precision, training, relu, has_res, has_bias,
     nbr = out_rows = masks = pl = None
     if need_dx:
         tc = bool(L.toda_spconv_uses_tensor_cores(cout, cin, kvol, precision))
-        if tc:
+        if tc and precision == CONV_BF16:
             wt, wtb = _repack(weight, True, rb.subm, True)
         else:
             wt = _repack(weight, True, rb.subm)
@@ -927,7 +929,7 @@ def _layer_backward(da, saved, rb, precision, training, relu, has_res, has_bias,
             nbr, pl = rb.nbr_bwd, rb.dgrad_plan
         else:
             nbr, out_rows, masks, pl = rb.nbr_bwd_sorted, rb.dgrad_order, rb.dgrad_tile_masks, rb.dgrad_plan
-        if not bf16:
+        if precision not in _TC_PRECISIONS:
             pl = None
         dx = torch.empty((rb.n_in, cin), dtype=torch.float32, device=dev)
         if addend is not None:

@@ -23,9 +23,10 @@ _precision = ops.CONV_FP32
 
 
 def set_conv_precision(p):
-    """'fp32' (FFMA, parity path) or 'bf16' (tcgen05 tensor cores, fp32 accumulate)."""
+    """'fp32' (FFMA, parity path), 'bf16' (tcgen05 tensor cores, bf16 operands, fp32 accumulate) or 'bf16x3' (the same
+    tensor-core kernels on split operands, three launches per product: fp32-class accuracy, rtol 1e-4 vs the oracle)."""
     global _precision
-    _precision = {"fp32": ops.CONV_FP32, "bf16": ops.CONV_BF16}[p] if isinstance(p, str) else int(p)
+    _precision = {"fp32": ops.CONV_FP32, "bf16": ops.CONV_BF16, "bf16x3": ops.CONV_BF16X3}[p] if isinstance(p, str) else int(p)
 
 
 def get_conv_precision():
@@ -103,7 +104,7 @@ def bn_act_tensor(x, bn, residual, relu):
     if _precision == ops.CONV_BF16:
         a, ab = ops.bn_act(x.features, bn, residual, relu, want_bf16=True, sums=x._bn_sums)
         return x.replace_feature(a, ab)
-    return x.replace_feature(ops.bn_act(x.features, bn, residual, relu))
+    return x.replace_feature(ops.bn_act(x.features, bn, residual, relu, sums=x._bn_sums))
 
 
 def conv_bn_act_tensor(x, conv, bn, residual, relu):
@@ -248,7 +249,7 @@ class SparseConvolution(SparseModule):
         x = x.canonical()
         rb, index_out = self._rulebook(x)
         # in tensor-core mode the epilogue also accumulates the statistics a following BatchNorm needs (train mode)
-        want_stats = _precision == ops.CONV_BF16 and self.training and torch.is_grad_enabled()
+        want_stats = _precision in (ops.CONV_BF16, ops.CONV_BF16X3) and self.training and torch.is_grad_enabled()
         if want_stats:
             y, sums = ops.sparse_conv(x.features, self.weight, self.bias, rb, _precision, x._features_bf16, want_stats=True)
         else:
