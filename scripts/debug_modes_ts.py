@@ -24,11 +24,12 @@ xb = x.to(torch.bfloat16)
 w = torch.randn(cout, 3, 3, 3, cin, device=dev) * 0.1
 L = _C.lib()
 L.toda_debug_set_mode.argtypes = [ctypes.c_int]
-bits = ["no loads", "no STTM", "no MMA", "no slab copies", "no epi stores", "no slab protocol", "no lidx"]
+bits = ["no loads", "no STTM", "no MMA", "no slab copies", "no epi stores", "no slab protocol", "no lidx", "late slab release"]
 print("conv %d->%d level %d n=%d tiles %d" % (cin, cout, level, n, (n + 127) // 128))
 y = torch.empty((n, cout), device=dev)
 wk = ops._repack(w, False, False)
-for mode in (0, 1, 2, 4, 8, 16, 32 | 8, 64, 31, 127, 0):
+modes = [int(m) for m in os.environ["TS_MODES"].split(",")] if os.environ.get("TS_MODES") else (0, 1, 2, 4, 8, 16, 32 | 8, 64, 31, 127, 0)
+for mode in modes:
     L.toda_debug_set_mode(mode)
     for _ in range(2): ops._conv_call(x, xb, cin, rb.nbr_fwd, n, 27, wk, cout, None, ops.CONV_BF16, tile_masks=rb.tile_masks, plan=rb.plan, y=y)
     torch.cuda.synchronize()

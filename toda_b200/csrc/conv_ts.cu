@@ -30,10 +30,15 @@ constexpr int kMaxKvol = 27;
 constexpr int kLidxBytes = 7168;                  // >= 27 * 128 * 2, 1024-multiple
 constexpr uint32_t kLidxNone = 0xFFFFu;           // no neighbour under this offset
 constexpr uint32_t kLidxGlobal = 0xFFFEu;         // neighbour exists but is not in the slab: read it from global memory
-constexpr int kGatherWarps = 16;                  // four warpgroups; a lone warp issues ~1 instruction per 5 cycles, so throughput comes from warps
+// Gather warps: kWGs warpgroups (per instantiation, TsCfg).  What bounds the gather is the number of dependent shared-memory
+// round trips per pair -- in the bursts where every gather warp loads at once a round trip costs ~500 cycles (timeline in
+// profiles/r02_conv_ts.md) -- and how many pairs are in flight.  Two variants, measured per layer width:
+//   * 4 warpgroups x 32 data registers: the two K blocks of a pair go through the same registers one after the other (768
+//     threads leave 80 registers per thread);
+//   * 2 warpgroups x 64 data registers: both blocks of a pair in flight at once (512 threads, up to 128 registers).
+// Same bytes in flight per SM either way; the second is ahead for 256-byte rows, the first for the narrow layers.
 // the warp scheduler favours high warp ids: the latency-critical gather warps get them
 constexpr int kWarpMma = 4, kWarpLoader = 5, kWarpB = 6, kWarpLoader2 = 7, kWarpGather0 = 8;
-constexpr int kThreads = 24 * 32;
 // A ring: pair slots of 2 x 32 TMEM columns (2 x 64 K elements) behind the two accumulators
 // Pair gp is produced by warpgroup gp % 4 into slot gp % kSlots.  Its barriers are NOT per slot but per pair index modulo
 // 16 (a_full / a_empty[gp & 15]): every barrier is then waited on by one warpgroup only, which sees each of its phases in turn
@@ -62,6 +67,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
         if (!done && ++spins > (1u << 20)) {           // a lost arrival must not hang the GPU box
             printf("conv_ts: mbarrier timeout smem=0x%x parity=%u block=%d warp=%d lane=%d\n", bar, parity, (int)blockIdx.x, (int)(threadIdx.x >> 5), (int)(threadIdx.x & 31));
+            __trap();
+        }
+    }
+}
+// wait of a role that is not on the critical path (epilogue, weight producer): probe, then really sleep -- a spinning warp
+// takes issue slots from the gather warp it shares a scheduler with (the epilogue's wait alone was 12 % of all instructions)
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity), "r"(0x4000u)
+            : "memory");
+        if (done) break;
+        __nanosleep(256);
+        if (++spins > (1u << 18)) {
+            printf("conv_ts: mbarrier timeout (relaxed) smem=0x%x parity=%u block=%d warp=%d\n", bar, parity, (int)blockIdx.x, (int)(threadIdx.x >> 5));
             __trap();
         }
     }
@@ -126,6 +151,16 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
 __device__ __forceinline__ void lds128(uint32_t addr, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d) {
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr));
 }
+// predicated 16-byte load: lanes without a neighbour keep their zeros and take no part in the access (no wavefront, no
+// bank conflict with the lanes that do read)
+__device__ __forceinline__ void lds128_if(uint32_t addr, uint32_t on, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %5, 0;\n\t"
+        "@p ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n\t}"
+        : "+r"(a), "+r"(b), "+r"(c), "+r"(d)
+        : "r"(addr), "r"(on));
+}
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     uint16_t v;
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
@@ -133,10 +168,13 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
 }
 
 template <int CIN, int COUT> struct TsCfg {
+    static constexpr int kWGs = CIN >= 128 ? 2 : 4;            // gather warpgroups
+    static constexpr bool kBoth = kWGs == 2;                   // both K blocks of a pair in flight (64 data registers)
+    static constexpr int kGatherWarps = 4 * kWGs;
+    static constexpr int kThreads = (8 + kGatherWarps) * 32;
     static constexpr int kRowBytes = CIN * 2;
     static constexpr int kRB = kRowBytes < 128 ? kRowBytes : 128;   // bytes of a row inside one swizzled slab half
     static constexpr int kHalves = kRowBytes / kRB;                  // 2 for 256-byte rows (two 128-byte column halves)
-    static constexpr int kNB = CIN == 128 ? 2 : 3;             // slab buffers (one per offset group in flight)
     // a slab caches 16-row BLOCKS of x (rows 16 b .. 16 b + 15), each brought in by one TMA box copy
     static constexpr int kCap = CIN == 128 ? 16 : (CIN == 64 ? 20 : 32);   // blocks per slab (<= 32: one loader lane per block)
     static constexpr int kHalfSlab = kCap * 16 * kRB;
@@ -149,13 +187,18 @@ template <int CIN, int COUT> struct TsCfg {
     static constexpr int kSB = kBRes ? kNkbMax : (COUT == 128 ? 4 : (COUT == 64 ? 6 : 8));
     static constexpr int kParts = CIN >= 64 ? 1 : 64 / CIN;    // kernel offsets per 64-element K block
     static constexpr int kPV = (CIN >= 64 ? 64 : CIN) / 8;     // 16-byte vectors per part
-    static constexpr int kSmemRaw = 1024 + kSB * kBStage + kNB * kSlab + 2 * kLidxBytes + 640 + 256;
+    // slab buffers (offset groups in flight): as many as fit, up to 4.  With 3 groups per tile and 3 buffers, group 0 of the next
+    // tile can only be fetched once every warp has let go of group 0 of this one; a 4th buffer takes that off the critical path.
+    static constexpr int kFixed = 1024 + kSB * kBStage + 2 * kLidxBytes + 640 + 256;
+    static constexpr int kNB = kFixed + 4 * kSlab <= 232448 ? 4 : (kFixed + 3 * kSlab <= 232448 ? 3 : 2);
+    static constexpr int kSmemRaw = kFixed + kNB * kSlab;
     // the kernel allocates all 512 TMEM columns: never let two CTAs share an SM (the second would wait in tcgen05.alloc)
     static constexpr int kSmem = kSmemRaw < 120 * 1024 ? 120 * 1024 : kSmemRaw;
     static_assert(kCap <= 32 && kSlab % 1024 == 0 && kBStage % 1024 == 0, "slab layout");
     static_assert(2 * COUT <= ARing<COUT>::kCol0 && ARing<COUT>::kCol0 + 64 * ARing<COUT>::kSlots <= 512, "TMEM map");
     static constexpr int kBBars = kBRes ? 1 : kSB;             // resident weights arrive on one barrier, once
     static_assert(kBBars <= 14, "barrier area");
+    static_assert(!kBRes || kNkbMax <= 32, "the MMA warp peels a 32-bit K-block mask when the weights are resident");
     // TMA swizzle of a slab row (hardware XORs the 16-byte chunk index with address bits 7..9 / 7..8 / 7): chunk q of slot s
     // lives at s * kRB + ((q ^ swz(s)) << 4); eight consecutive slots then hit eight different 16-byte bank groups
     __device__ static __forceinline__ uint32_t swz(uint32_t s) { return kRB == 128 ? (s & 7u) : (kRB == 64 ? ((s >> 1) & 3u) : ((s >> 2) & 1u)); }
@@ -171,10 +214,10 @@ template <int CIN, int COUT> struct TsCfg {
           "r"(v[30]), "r"(v[31])                                                                                                    \
         : "memory")
 
-// Roles (16 warps): 0-3 epilogue, 4 MMA issuer, 5 + 7 slab loaders, 6 weight producer, 8-15 gather (two warpgroups,
+// Roles: warps 0-3 epilogue, 4 MMA issuer, 5 + 7 slab loaders, 6 weight producer, 8.. gather (TsCfg::kWGs warpgroups,
 // thread = tile row = TMEM lane).
 template <int CIN, int COUT>
-__global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfloat16 *__restrict__ xb, const int *__restrict__ nbr,
+__global__ void __launch_bounds__((TsCfg<CIN, COUT>::kThreads), 1) conv_ts_fwd_kernel(const __nv_bfloat16 *__restrict__ xb, const int *__restrict__ nbr,
                                                                   int n_out, int kvol, const uint16_t *__restrict__ lidx,
                                                                   const int *__restrict__ prow, const int *__restrict__ pcnt,
                                                                   int ngroups, int cap,
@@ -189,7 +232,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
     constexpr bool BRES = C::kBRes;
     constexpr int kASlots = ARing<COUT>::kSlots, kACol0 = ARing<COUT>::kCol0;
     extern __shared__ uint8_t smem_raw[];
-    const uint32_t raw = smem_u32(smem_raw);
+    uint32_t raw;     // (volatile: the compiler otherwise re-derives the shared window base from SR_CgaCtaId at every use)
+    asm volatile("mov.u32 %0, %1;" : "=r"(raw) : "r"(smem_u32(smem_raw)));
     const uint32_t base = (raw + 1023u) & ~1023u;          // B stages: SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t slab_base = base + SB * C::kBStage;
     const uint32_t lidx_base = slab_base + NB * C::kSlab;
@@ -197,9 +241,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
     const uint32_t a_full = bar_base, a_empty = bar_base + 128;              // 16 + 16
     const uint32_t b_full = bar_base + 256, b_empty = bar_base + 368;         // 14 + 14
     const uint32_t acc_full = bar_base + 480, acc_empty = bar_base + 496;     // 2 + 2
-    const uint32_t slab_full = bar_base + 512, slab_empty = bar_base + 536;   // 3 + 3
-    const uint32_t lidx_full = bar_base + 560, lidx_empty = bar_base + 576;   // 2 + 2
-    const uint32_t tmem_slot = bar_base + 592;
+    const uint32_t slab_full = bar_base + 512, slab_empty = bar_base + 544;   // 4 + 4
+    const uint32_t lidx_full = bar_base + 576, lidx_empty = bar_base + 592;   // 2 + 2
+    const uint32_t tmem_slot = bar_base + 608;
     const uint32_t zero_base = bar_base + 640;               // 256 zero bytes: the row read for a missing neighbour
     volatile uint32_t *tmem_slot_ptr = (volatile uint32_t *)(smem_raw + (tmem_slot - raw));
 
@@ -229,6 +273,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
         return cm ? cm : 1ull;
     };
     auto kb_mask_of = [&](int t) -> unsigned long long { return kb_mask_from(load_om(t)); };
+    // Active K blocks as a list held across the warp: lane r keeps the K block of rank r (and r + 32 when a tile can have more
+    // than 32 K blocks).  The roles used to peel the mask bit by bit -- ~42 instructions of 64-bit arithmetic per pair, run by
+    // every gather warp for all the pairs it skips as well: 18 % of all instructions the kernel issued and most of the gather
+    // warps' latency per pair (ncu source view, profiles/r02_conv_ts.md).  Now a pair costs two shuffles.
+    auto kb_list = [&](unsigned long long cm, int &p0, int &p1) {
+        const uint32_t lo = (uint32_t)cm, hi = (uint32_t)(cm >> 32);
+        const int nlo = __popc(lo);
+        p0 = lane < nlo ? (int)__fns(lo, 0, lane + 1) : -1;
+        p1 = -1;
+        if (CIN > 64) {
+            const int nhi = __popc(hi);
+            if (lane >= nlo && lane - nlo < nhi) p0 = 32 + (int)__fns(hi, 0, lane - nlo + 1);
+            const int r1 = lane + 32 - nlo;
+            if (r1 >= 0 && r1 < nhi) p1 = 32 + (int)__fns(hi, 0, r1 + 1);
+        }
+    };
+    auto kb_at = [&](int p0, int p1, int rank) -> int {
+        if (CIN > 64) {
+            const int a = __shfl_sync(0xffffffffu, p0, rank & 31), b = __shfl_sync(0xffffffffu, p1, rank & 31);
+            return rank < 32 ? a : b;
+        }
+        return __shfl_sync(0xffffffffu, p0, rank);
+    };
 
     if (tid == 0) {
         for (int s = 0; s < kABars; ++s) {
@@ -243,11 +310,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
             mbar_init(acc_full + 8 * b, 1);
             mbar_init(acc_empty + 8 * b, 4);       // the four epilogue warps
             mbar_init(lidx_full + 8 * b, 1);
-            mbar_init(lidx_empty + 8 * b, kGatherWarps);
+            mbar_init(lidx_empty + 8 * b, C::kGatherWarps);
         }
         for (int b = 0; b < NB; ++b) {
             mbar_init(slab_full + 8 * b, 1);       // arrive.expect_tx by the loader; the TMA box copies complete the bytes
-            mbar_init(slab_empty + 8 * b, kGatherWarps);
+            mbar_init(slab_empty + 8 * b, C::kGatherWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -271,75 +338,107 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
 
     if (warp >= kWarpGather0) {
         // ------------------------------------------------------------------ gather warps: thread = tile row = TMEM lane
-        // The active K blocks of a tile are dealt out in pairs: warpgroup 0 takes pairs 0, 2, ..., warpgroup 1 pairs 1, 3, ...
-        // A pair costs one round of barrier waits / tcgen05.wait::st / arrivals and keeps 2 x 128 bytes per thread in flight.
-        const int wg = (warp - kWarpGather0) >> 2;
-        const int row = (warp & 3) * 32 + lane;
-        const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kACol0;
-        int gbase = 0, gpbase = 0, it = 0;              // global index of this tile's first active K block / first pair
+        // The active K blocks of a tile are dealt out in pairs, pair gp to warpgroup gp % 4.  A pair costs one round of barrier
+        // waits / tcgen05.wait::st / arrivals and keeps 2 x 128 bytes per thread in flight.  This loop is instruction-latency
+        // bound (the warps share four schedulers at ~57 % issue utilisation, profiles/r02_conv_ts.md), so everything that does
+        // not depend on the pair is computed once per tile: unsigned arithmetic only, no division by the ring sizes, barrier
+        // addresses and phases of the tile's slabs kept in registers.
+        const uint32_t wg = (uint32_t)(warp - kWarpGather0) >> 2;
+        const uint32_t row = (uint32_t)(warp & 3) * 32u + (uint32_t)lane;
+        const uint32_t t_lane = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + kACol0;
+        const uint32_t ugs = (uint32_t)gs, ugs2 = (uint32_t)gs2, ukvol = (uint32_t)kvol;
+        uint32_t gpbase = 0, it = 0;                    // global index of this tile's first pair
+        uint32_t uq = 0, ur = 0;                        // the tile's first (tile, group) unit is number uq * NB + ur of this CTA
+#ifdef TODA_TS_TIMELINE
+        int gbase = 0;
+#endif
         uint32_t om_next = load_om(blockIdx.x);
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-            const int ib = it & 1;
+            const uint32_t ib = it & 1u;
             const uint32_t om = om_next;
             om_next = load_om(t + gridDim.x);
             TS_DBG(tid == 256, 22, it);
-            if (!(xmode & 64)) mbar_wait(lidx_full + 8 * ib, (it >> 1) & 1);
+            mbar_wait(lidx_full + 8 * ib, (it >> 1) & 1u);
             TS_DBG(tid == 256, 23, it);
-            const uint32_t lidx_tile = lidx_base + ib * kLidxBytes + 2 * row;
-            const int unit0 = it * ngroups;             // (tile, group) units are numbered consecutively per CTA
-            int gwait = 0, gdone = 0;                   // groups of this tile whose slab this warp has waited for / released
-            auto wait_group = [&](int grp) {
-                if (xmode & 32) return;
-                while (gwait <= grp) {
-                    const int u = unit0 + gwait;
-                    mbar_wait(slab_full + 8 * (u % NB), (u / NB) & 1);
-                    ++gwait;
-                }
+            const uint32_t lidx_tile = lidx_base + ib * kLidxBytes + 2u * row;
+            // slab buffer, barrier offset and phase parity of the tile's (up to three) offset groups
+            uint32_t sbuf[3], sbar[3], spar[3];
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                uint32_t r = ur + (uint32_t)g;
+                const uint32_t wrap = r >= (uint32_t)NB ? 1u : 0u;
+                r -= wrap * (uint32_t)NB;
+                sbuf[g] = slab_base + r * (uint32_t)C::kSlab;
+                sbar[g] = 8u * r;
+                spar[g] = (uq + wrap) & 1u;
+            }
+            uint32_t gwait = 0, gdone = 0;              // groups of this tile whose slab this warp has waited for / released
+            auto wait_group = [&](uint32_t grp) {       // the slabs of groups 0..grp have landed
+                if (gwait > grp) return;
+#pragma unroll
+                for (int g = 0; g < 3; ++g)
+                    if ((uint32_t)g >= gwait && (uint32_t)g <= grp) mbar_wait(slab_full + sbar[g], spar[g]);
+                gwait = grp + 1u;
             };
-            auto release_below = [&](int grp_end) {
+            auto release_below = [&](uint32_t grp_end) {
                 // (a warp waits for a slab before releasing it even if it never read it: its arrival must not land in
-                // the barrier phase of the slab's previous use)
-                while (gdone < grp_end && !(xmode & 32)) {
-                    wait_group(gdone);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(slab_empty + 8 * ((unit0 + gdone) % NB));
-                    ++gdone;
-                }
+                // the barrier phase of the slab's previous use.  One group at a time: with fewer buffers than groups the
+                // slab of a later group is only fetched once an earlier one has been handed back.)
+                if (gdone >= grp_end) return;
+#pragma unroll
+                for (int g = 0; g < 3; ++g)
+                    if ((uint32_t)g >= gdone && (uint32_t)g < grp_end) {
+                        if ((uint32_t)g >= gwait) {
+                            mbar_wait(slab_full + sbar[g], spar[g]);
+                            gwait = (uint32_t)g + 1u;
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(slab_empty + sbar[g]);
+                    }
+                gdone = grp_end;
             };
-            // Branch-free fast path: a row without a neighbour reads the all-zero row kept at slot `cap` of every slab
-            // (all such lanes hit one address: a broadcast); the table entries of the block are fetched first, then
-            // every 16-byte piece.  Returns true if some entry must be read from global memory instead (fix_block).
-            auto load_block = [&](int kb, uint32_t (&v)[32]) -> bool {
-                uint32_t li[PARTS];
+            // Branch-free fast path: the table entries of both blocks of a pair are fetched first (load_li), then every
+            // 16-byte piece of both blocks by predicated loads (load_data): a row without a neighbour keeps zero registers and
+            // issues no shared-memory access -- 44 % of the entries of a stride-1 table are empty.  load_data returns true if
+            // some entry must be read from global memory instead (fix_block).
+            auto load_li = [&](uint32_t kb, bool on, uint32_t (&li)[PARTS]) {
 #pragma unroll
                 for (int part = 0; part < PARTS; ++part) {
-                    const int k = CIN == 128 ? (kb >> 1) : kb * PARTS + part;
-                    li[part] = k < kvol ? lds_u16(lidx_tile + (uint32_t)k * (kTileM * 2)) : kLidxNone;
+                    const uint32_t k = CIN == 128 ? (kb >> 1) : kb * PARTS + part;
+                    li[part] = kLidxNone;
+                    if (on && (PARTS == 1 || k < ukvol)) li[part] = lds_u16(lidx_tile + k * (kTileM * 2));
                 }
+            };
+            auto load_data = [&](uint32_t kb, const uint32_t (&li)[PARTS], uint32_t (&v)[32]) -> bool {
                 bool fix = false;
 #pragma unroll
                 for (int part = 0; part < PARTS; ++part) {
-                    const int k = CIN == 128 ? (kb >> 1) : kb * PARTS + part;
-                    const int grp = (int)(k >= gs) + (int)(k >= gs2);
+                    const uint32_t k = CIN == 128 ? (kb >> 1) : kb * PARTS + part;
                     const uint32_t sl = li[part];
                     const bool hit = sl < kLidxGlobal;
-                    const uint32_t buf = slab_base + (uint32_t)((unit0 + grp) % NB) * C::kSlab + (CIN == 128 ? (uint32_t)(kb & 1) * C::kHalfSlab : 0u);
-                    const uint32_t src = hit ? buf + sl * C::kRB : zero_base;
-                    const uint32_t x = hit ? C::swz(sl) : 0u;
+                    uint32_t buf = k >= ugs2 ? sbuf[2] : (k >= ugs ? sbuf[1] : sbuf[0]);
+                    if (CIN == 128) buf += (kb & 1u) * (uint32_t)C::kHalfSlab;
+                    // chunk q of slot s lives at s * kRB + ((q ^ swz(s)) << 4); the row start is kRB-aligned, so the swizzle
+                    // is one XOR of the row address per 16-byte piece
+                    const uint32_t src = buf + sl * (uint32_t)C::kRB + (C::swz(sl) << 4);
+                    const uint32_t on = hit ? 1u : 0u;
 #pragma unroll
-                    for (int q = 0; q < PV; ++q)
-                        lds128(src + (((uint32_t)q ^ x) << 4), v[(part * PV + q) * 4], v[(part * PV + q) * 4 + 1], v[(part * PV + q) * 4 + 2],
-                               v[(part * PV + q) * 4 + 3]);
+                    for (int q = 0; q < PV; ++q) {
+                        uint32_t &r0 = v[(part * PV + q) * 4], &r1 = v[(part * PV + q) * 4 + 1], &r2 = v[(part * PV + q) * 4 + 2],
+                                 &r3 = v[(part * PV + q) * 4 + 3];
+                        r0 = r1 = r2 = r3 = 0u;
+                        lds128_if(src ^ ((uint32_t)q << 4), on, r0, r1, r2, r3);
+                    }
                     fix |= sl == kLidxGlobal;
                 }
                 return fix;
             };
-            auto fix_block = [&](int kb, uint32_t (&v)[32]) {
+            auto fix_block = [&](uint32_t kb, const uint32_t (&li)[PARTS], uint32_t (&v)[32]) {
 #pragma unroll
                 for (int part = 0; part < PARTS; ++part) {
-                    const int k = CIN == 128 ? (kb >> 1) : kb * PARTS + part;
-                    const uint32_t half = CIN == 128 ? (uint32_t)(kb & 1) * 128u : 0u;
-                    if (k < kvol && lds_u16(lidx_tile + (uint32_t)k * (kTileM * 2)) == kLidxGlobal) {
+                    const uint32_t k = CIN == 128 ? (kb >> 1) : kb * PARTS + part;
+                    const uint32_t half = CIN == 128 ? (kb & 1u) * 128u : 0u;
+                    if (li[part] == kLidxGlobal) {
                         const int gi = __ldg(nbr + (size_t)k * n_out + (size_t)t * kTileM + row);
                         const uint4 *src = (const uint4 *)((const char *)xb + (size_t)gi * C::kRowBytes + half);
 #pragma unroll
@@ -351,68 +450,90 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
                     }
                 }
             };
-            unsigned long long cm = kb_mask_from(om);
-            const int nact = __popcll(cm);
+            const unsigned long long cm = kb_mask_from(om);
+            const uint32_t nact = (uint32_t)__popcll(cm), npairs = (nact + 1u) >> 1;
+            int kl0, kl1;
+            kb_list(cm, kl0, kl1);
 #ifdef TODA_TS_TIMELINE
             if (dbg && blockIdx.x == 0 && tid == 256 && it < 256) dbg[10 * 256 + it] = gbase;
 #endif
-            int j = 0;
-            while (cm) {
-                const int kbA = __ffsll((long long)cm) - 1;
-                cm &= cm - 1;
-                int kbB = -1;
-                if (cm) {
-                    kbB = __ffsll((long long)cm) - 1;
-                    cm &= cm - 1;
-                }
-                const int gA = gbase + j;
-                const int pj = j >> 1;
-                const int gp = gpbase + pj;             // global pair index: A slot gp % kASlots (two 32-column blocks)
-                const int aslot = gp % kASlots;
-                j += 2;
-                if ((gp & 3) != wg) continue;
+            // this warpgroup's pairs of the tile: global pair index gp = gpbase + pj with gp % kWGs == wg (kWGs is 2 or 4)
+            for (uint32_t pj = (wg - gpbase) & (uint32_t)(C::kWGs - 1); pj < npairs; pj += (uint32_t)C::kWGs) {
+                const uint32_t kbA = (uint32_t)kb_at(kl0, kl1, (int)(2u * pj));
+                const uint32_t kbB = (uint32_t)kb_at(kl0, kl1, (int)((2u * pj + 1u) & 63u));
+                const bool two = 2u * pj + 1u < nact;
+#ifdef TODA_TS_TIMELINE
+                const int gA = gbase + 2 * (int)pj;
+#endif
+                const uint32_t gp = gpbase + pj;        // global pair index: A slot gp % kASlots (two 32-column blocks)
+                const uint32_t aslot = gp % (uint32_t)kASlots;
                 TS_DBG((tid & 127) == 0, 0, gA);
-                const int k_first = CIN == 128 ? (kbA >> 1) : kbA * PARTS;
-                release_below((int)(k_first >= gs) + (int)(k_first >= gs2));    // slabs of earlier groups are no longer read by this warp
+                uint32_t liA[PARTS], liB[PARTS];
+                load_li(kbA, true, liA);
+                load_li(kbB, two, liB);
+                const uint32_t k_first = CIN == 128 ? (kbA >> 1) : kbA * PARTS;
+                release_below((k_first >= ugs ? 1u : 0u) + (k_first >= ugs2 ? 1u : 0u));   // slabs of earlier groups are no longer read by this warp
                 TS_DBG((tid & 127) == 0, 1, gA);
                 {
-                    const int kb_last = kbB >= 0 ? kbB : kbA;
-                    const int k_last = min(CIN == 128 ? (kb_last >> 1) : kb_last * PARTS + PARTS - 1, kvol - 1);
-                    wait_group((int)(k_last >= gs) + (int)(k_last >= gs2));
+                    const uint32_t kb_last = two ? kbB : kbA;
+                    const uint32_t k_last = min(CIN == 128 ? (kb_last >> 1) : kb_last * PARTS + PARTS - 1, ukvol - 1u);
+                    wait_group((k_last >= ugs ? 1u : 0u) + (k_last >= ugs2 ? 1u : 0u));
                 }
-                // the two K blocks of the pair go through the same 32 registers one after the other (the A slot is waited
-                // for only after the first block's loads are in flight: the barrier probe overlaps them)
+                // (the A slot is waited for while the loads are in flight: the barrier probe overlaps them)
                 uint32_t va[32];
-                bool fix = load_block(kbA, va);
-                if (gp >= kASlots) {         // the pair that used this slot before (gp - kASlots) has been consumed
-                    mbar_wait(a_empty + 8 * ((gp - kASlots) & (kABars - 1)), ((gp - kASlots) / kABars) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                }
-                TS_DBG((tid & 127) == 0, 12, gA);
-                if (__any_sync(0xffffffffu, fix)) fix_block(kbA, va);
-                __syncwarp();
-                TS_STTM_X32(t_lane + aslot * 64, va);
-                if (kbB >= 0) {
-                    fix = load_block(kbB, va);
-                    if (__any_sync(0xffffffffu, fix)) fix_block(kbB, va);
+                bool fixA = load_data(kbA, liA, va);
+                if (C::kBoth) {
+                    uint32_t vb[32];
+                    bool fixB = load_data(kbB, liB, vb);
+                    if (gp >= (uint32_t)kASlots) {      // the pair that used this slot before (gp - kASlots) has been consumed
+                        const uint32_t pg = gp - (uint32_t)kASlots;
+                        mbar_wait(a_empty + 8u * (pg & (kABars - 1)), (pg / kABars) & 1u);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    TS_DBG((tid & 127) == 0, 12, gA);
+                    if (__any_sync(0xffffffffu, fixA || fixB)) {
+                        fix_block(kbA, liA, va);
+                        fix_block(kbB, liB, vb);
+                    }
                     __syncwarp();
-                    TS_STTM_X32(t_lane + aslot * 64 + 32, va);
+                    TS_STTM_X32(t_lane + aslot * 64u, va);
+                    if (two) TS_STTM_X32(t_lane + aslot * 64u + 32u, vb);
+                } else {
+                    if (gp >= (uint32_t)kASlots) {
+                        const uint32_t pg = gp - (uint32_t)kASlots;
+                        mbar_wait(a_empty + 8u * (pg & (kABars - 1)), (pg / kABars) & 1u);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    TS_DBG((tid & 127) == 0, 12, gA);
+                    if (__any_sync(0xffffffffu, fixA)) fix_block(kbA, liA, va);
+                    __syncwarp();
+                    TS_STTM_X32(t_lane + aslot * 64u, va);
+                    if (two) {                          // (the table entries of block B were fetched with those of block A)
+                        fixA = load_data(kbB, liB, va);
+                        if (__any_sync(0xffffffffu, fixA)) fix_block(kbB, liB, va);
+                        __syncwarp();
+                        TS_STTM_X32(t_lane + aslot * 64u + 32u, va);
+                    }
                 }
                 TS_DBG((tid & 127) == 0, 2, gA);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(a_full + 8 * (gp & (kABars - 1)));
+                if (lane == 0) mbar_arrive(a_full + 8u * (gp & (kABars - 1)));
                 TS_DBG((tid & 127) == 0, 3, gA);
                 TS_DBG(lane == 0, 16 + (warp - kWarpGather0), gA);
             }
-            gbase += nact;
-            gpbase += (nact + 1) >> 1;
+#ifdef TODA_TS_TIMELINE
+            gbase += (int)nact;
+#endif
+            gpbase += npairs;
             TS_DBG(tid == 256, 20, it);
-            release_below(ngroups);
+            release_below((uint32_t)ngroups);
             TS_DBG(tid == 256, 21, it);
+            ur += (uint32_t)ngroups;
+            while (ur >= (uint32_t)NB) { ur -= (uint32_t)NB; ++uq; }
             __syncwarp();
-            if (lane == 0 && !(xmode & 64)) mbar_arrive(lidx_empty + 8 * ib);
+            if (lane == 0) mbar_arrive(lidx_empty + 8 * ib);
         }
     } else if (warp < kWarpMma) {
         // ------------------------------------------------------------------ epilogue (warps 0..3)
@@ -423,7 +544,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int ab = it & 1;
-            mbar_wait(acc_full + 8 * ab, (it >> 1) & 1);
+            mbar_wait_relaxed(acc_full + 8 * ab, (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row = t * kTileM + q * 32 + lane;          // TMEM lane = tile row
             // row of y this tile row is written to (class-sorted dgrad launches scatter back to canonical rows)
@@ -495,20 +616,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
             TS_DBG(lane == 0, 15, it);
             const uint32_t d_tmem = tmem_base + ab * COUT;
             uint32_t accumulate = 0;
-            unsigned long long cm = kb_mask_from(om);
-            const int nact = __popcll(cm);
-            int j = 0;
-            while (cm) {
-                const int kbA = __ffsll((long long)cm) - 1;
-                cm &= cm - 1;
-                int kbB = -1;
-                if (cm) {
-                    kbB = __ffsll((long long)cm) - 1;
-                    cm &= cm - 1;
+            const unsigned long long cm = kb_mask_from(om);
+            const int nact = __popcll(cm), npairs = (nact + 1) >> 1;
+            // resident weights are addressed by K block (at most 14 of them: a 32-bit mask peeled with two instructions per
+            // block), streamed ones by ring position.  No shuffles here: they queue behind the gather warps' shared-memory loads.
+            uint32_t m32 = (uint32_t)cm;
+            for (int pj = 0; pj < npairs; ++pj) {
+                const int gA = gbase + 2 * pj;
+                const int n = 2 * pj + 1 < nact ? 2 : 1;
+                int kbA = 0, kbB = 0;
+                if (BRES) {
+                    kbA = __ffs((int)m32) - 1;
+                    m32 &= m32 - 1u;
+                    kbB = __ffs((int)m32) - 1;
+                    m32 &= m32 - 1u;
                 }
-                const int gA = gbase + j;
-                const int n = kbB >= 0 ? 2 : 1;
-                j += 2;
                 const int aslot = gp % kASlots;
                 mbar_wait(a_full + 8 * (gp & (kABars - 1)), (gp / kABars) & 1);
                 if (!BRES) {
@@ -609,7 +731,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_ts_fwd_kernel(const __nv_bfl
                     for (unsigned long long cm = cm0; cm; cm &= cm - 1, ++gg) {
                         const int kb = __ffsll((long long)cm) - 1;
                         const int stage = gg % SB, use = gg / SB;
-                        if (use > 0) mbar_wait(b_empty + 8 * stage, (use - 1) & 1);
+                        if (use > 0) mbar_wait_relaxed(b_empty + 8 * stage, (use - 1) & 1);
                         TS_DBG(true, 13, gg);
                         mbar_arrive_expect_tx(b_full + 8 * stage, C::kBStage);
                         tma_load_2d(base + stage * C::kBStage, &map_w, kb * 64, 0, b_full + 8 * stage);
@@ -738,7 +860,7 @@ int launch_ts(const __nv_bfloat16 *xb, int n_in, const int32_t *nbr, int n_out, 
         TODA_CUDA_OK(cudaFuncSetAttribute(conv_ts_fwd_kernel<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
         attr_set = true;
     }
-    conv_ts_fwd_kernel<CIN, COUT><<<grid, kThreads, C::kSmem, st>>>(xb, nbr, n_out, kvol, plan.lidx, plan.rows, plan.cnt, plan.ngroups,
+    conv_ts_fwd_kernel<CIN, COUT><<<grid, C::kThreads, C::kSmem, st>>>(xb, nbr, n_out, kvol, plan.lidx, plan.rows, plan.cnt, plan.ngroups,
                                                                    plan.cap, map_x, map_w, bias, addend, y, out_rows, tile_masks, bn_sums,
                                                                    num_tiles, conv_tc_debug_timeline(), conv_tc_debug_mode());
     TODA_LAUNCH_OK();
