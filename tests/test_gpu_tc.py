@@ -287,7 +287,8 @@ def test_backbone_x3_vs_reference_golden():
     Backward: a 1e-5 perturbation is enough to flip ReLU masks of activations that sit at the kink, and one flipped mask
     moves the whole gradient field by ~0.5 % (measured on the stage-2 golden, tests/test_gpu_parity.py), so the gradient
     ARITHMETIC is compared with the masks frozen (recorded in an fp32 FFMA pass, imposed on the bf16x3 pass): relative L2
-    <= 1e-3 for d loss / d voxel_features and every parameter gradient (the bf16 mode's bound is 3e-2); against the
+    <= 5e-4 for d loss / d voxel_features and every conv-weight / BatchNorm gradient (measured 2.6e-5 and 9.5e-5; the bf16
+    mode's bound is 3e-2); against the
     golden, with its own masks, the gradients are held to relative L2 <= 2e-2."""
     import toda_b200.pcdet_plugin as P
     from toda_b200 import ops
@@ -330,7 +331,10 @@ def test_backbone_x3_vs_reference_golden():
         ops.set_relu_mask_tape(None)
         G.set_conv_precision("fp32")
     e_dx = rl2(res["bf16x3"]["dvoxel_features"], res["fp32"]["dvoxel_features"])
-    e_p = {k: rl2(res["bf16x3"]["grads"][k], v) for k, v in res["fp32"]["grads"].items()}
+    # (the bias of a convolution that feeds a batch-statistics BatchNorm has an identically zero gradient: both passes hold
+    # rounding noise there, which has no relative error to speak of)
+    e_p = {k: rl2(res["bf16x3"]["grads"][k], v) for k, v in res["fp32"]["grads"].items()
+           if v.ndim == 5 or ".bn" in k or k.endswith(".1.weight") or k.endswith(".1.bias")}
     print("bf16x3 vs fp32, masks frozen: d voxel_features rel-L2 %.3e; parameter grads max %.3e" % (e_dx, max(e_p.values())))
-    assert e_dx <= 1e-3
-    assert max(e_p.values()) <= 1e-3, max(e_p.items(), key=lambda kv: kv[1])
+    assert e_dx <= 5e-4          # measured 2.6e-5
+    assert max(e_p.values()) <= 5e-4, max(e_p.items(), key=lambda kv: kv[1])    # measured 9.5e-5
