@@ -220,7 +220,7 @@ def run_ours(args, rank, world, local_rank):
     vfe, net, hc = build_hot_path(device, args.precision)
     bucket = FlatGradBucket(net.parameters())
     train = WORKLOADS[WORKLOAD]["train"]
-    hosts = host_batches(rank, POOL, device)
+    hosts = host_batches(rank if args.data_rank is None else args.data_rank, POOL, device)
     devs = [(p.to(device), o.to(device)) for p, o in hosts]
     cot = None
 
@@ -392,11 +392,12 @@ def run_ours(args, rank, world, local_rank):
         return None
     # ---- roofline pass (rank 0): per-call device times of one more step, not part of `value` ----------------
     peaks = load_peaks()
-    step(*devs[0], reduce=False)                # (re-warms the allocator for the in-line call sequence)
-    torch.cuda.synchronize()
-    ops.profile_begin()
-    loss, bd = step(*devs[0], reduce=False)     # rank 0 only: no collective inside this pass
-    prof = ops.profile_end()
+    with bucket.no_sync():                      # rank 0 only: the gradient hooks must not launch a collective here
+        step(*devs[0], reduce=False)            # (re-warms the allocator for the in-line call sequence)
+        torch.cuda.synchronize()
+        ops.profile_begin()
+        loss, bd = step(*devs[0], reduce=False)
+        prof = ops.profile_end()
     roof, layers = roofline_from_profile(prof, bd, peaks, ms / args.steps)
     line = dict(metric=WORKLOADS[WORKLOAD]["metric"], value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
@@ -569,6 +570,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("TODA_CONV_PRECISION", "bf16"), choices=["fp32", "bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--data-rank", type=int, default=None, help="debug: use the synthetic frames rank R of a multi-GPU run would get")
     ap.add_argument("--workload", default="nus_0075", choices=sorted(WORKLOADS),
                     help="default = BASELINE.json configs[2]; waymo_second = configs[1]; toda_stage2 = configs[3]")
     args = ap.parse_args()

@@ -236,6 +236,13 @@ int toda_bn_eval_coeffs(const float *gamma, const float *beta, const float *runn
 /* a_bf16 / dy_bf16 (optional, may be NULL): bf16 copies written by the same pass, consumed as tensor-core operands. */
 int toda_bn_apply(const float *y, int n, int channels, const float *scale, const float *shift, const float *residual,
                   int relu, float *a, void *a_bf16, void *stream);
+/* finalize_sums + apply in ONE launch (training mode, statistics from the convolution's epilogue): every thread derives the
+ * coefficients of its four channels from `sums`; scale / shift / save_mean / save_rstd are still written for the backward
+ * pass and the running statistics updated.  Same results, bit for bit, as the two calls it replaces. */
+int toda_bn_apply_sums(const float *y, int n, int channels, const double *sums, const float *gamma, const float *beta,
+                       float eps, float momentum, float *running_mean, float *running_var, float *scale, float *shift,
+                       float *save_mean, float *save_rstd, const float *residual, int relu, float *a, void *a_bf16,
+                       void *stream);
 int toda_bn_bwd(const float *da, const float *a, const float *y, int n, int channels, const float *gamma,
                 const float *save_mean, const float *save_rstd, int relu, int training, float *dy, void *dy_bf16,
                 float *dresidual, float *dgamma, float *dbeta, void *workspace, size_t workspace_bytes, void *stream);

@@ -89,3 +89,38 @@ def test_flat_bucket_allreduce_world2():
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert out[0][0] == 100 and out[1][0] == 104            # disjoint frame ranges per rank
     assert abs(out[0][1] - out[1][1]) < 1e-6                # identical averaged gradients on both ranks
+
+
+def _worker_no_sync(rank, world, port, out):
+    """A backward pass that only rank 0 runs (bench.py's per-kernel roofline pass) must not launch a collective: inside
+    no_sync() the gradient hooks stay quiet, and the next synchronised step still pairs up on both ranks."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+    bucket = FlatGradBucket(net.parameters(), bucket_bytes=64)
+    if rank == 0:
+        with bucket.no_sync():
+            bucket.zero()
+            net(torch.ones(4, 5)).sum().backward()
+            bucket.all_reduce_mean()             # a no-op inside no_sync
+            assert not bucket._work
+    bucket.zero()
+    x = torch.full((4, 5), float(rank + 1))
+    net(x).sum().backward()
+    local = torch.cat([p.grad.flatten() for p in net.parameters()]).clone()
+    bucket.all_reduce_mean()
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    assert torch.allclose(bucket.flat, sum(gathered) / world, rtol=1e-6, atol=1e-7)
+    out[rank] = float(bucket.flat.sum())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_no_sync_pass_on_one_rank():
+    world, port = 2, _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_worker_no_sync, args=(world, port, out), nprocs=world, join=True)
+    assert abs(out[0] - out[1]) < 1e-6

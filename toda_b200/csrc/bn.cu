@@ -145,6 +145,28 @@ __device__ __forceinline__ void warp_sum_partials(const double *__restrict__ par
     s = a; ss = b;
 }
 
+// BatchNorm coefficients of one channel from its sums (fp64).  One definition for the finalize kernel and for the fused
+// statistics+apply kernel below, with explicit roundings so that both produce the same bits.
+__device__ __forceinline__ void bn_coeffs(double s, double ss, int n, float g, float bt, float eps, float &scale, float &shift,
+                                          float &meanf, float &rstd, double &var) {
+    const double mean = n > 0 ? s / n : 0.0;
+    var = n > 0 ? ss / n - mean * mean : 0.0;
+    if (var < 0.0) var = 0.0;
+    rstd = (float)(1.0 / sqrt(var + (double)eps));
+    meanf = (float)mean;
+    scale = __fmul_rn(g, rstd);
+    shift = __fsub_rn(bt, __fmul_rn(__fmul_rn(meanf, g), rstd));
+}
+
+__device__ __forceinline__ void bn_update_running(float *running_mean, float *running_var, int ch, float momentum, float meanf,
+                                                  double var, int n) {
+    if (running_mean) running_mean[ch] = __fadd_rn(__fmul_rn(1.f - momentum, running_mean[ch]), __fmul_rn(momentum, meanf));
+    if (running_var) {
+        const double unbiased = n > 1 ? var * n / (n - 1) : var;
+        running_var[ch] = __fadd_rn(__fmul_rn(1.f - momentum, running_var[ch]), __fmul_rn(momentum, (float)unbiased));
+    }
+}
+
 __global__ void bn_finalize_kernel(const double *__restrict__ partial, int nblocks, int n, int c,
                                    const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float momentum,
                                    float *running_mean, float *running_var, float *scale, float *shift, float *save_mean,
@@ -154,20 +176,14 @@ __global__ void bn_finalize_kernel(const double *__restrict__ partial, int nbloc
     double s, ss;
     warp_sum_partials(partial, nblocks, c, ch, s, ss);
     if ((threadIdx.x & 31) != 0) return;
-    double mean = n > 0 ? s / n : 0.0;
-    double var = n > 0 ? ss / n - mean * mean : 0.0;
-    if (var < 0.0) var = 0.0;
-    float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    float g = gamma ? gamma[ch] : 1.f, bt = beta ? beta[ch] : 0.f;
-    scale[ch] = g * rstd;
-    shift[ch] = bt - (float)mean * g * rstd;
-    if (save_mean) save_mean[ch] = (float)mean;
+    float sc, sh, meanf, rstd;
+    double var;
+    bn_coeffs(s, ss, n, gamma ? gamma[ch] : 1.f, beta ? beta[ch] : 0.f, eps, sc, sh, meanf, rstd, var);
+    scale[ch] = sc;
+    shift[ch] = sh;
+    if (save_mean) save_mean[ch] = meanf;
     if (save_rstd) save_rstd[ch] = rstd;
-    if (running_mean) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)mean;
-    if (running_var) {
-        double unbiased = n > 1 ? var * n / (n - 1) : var;
-        running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
-    }
+    bn_update_running(running_mean, running_var, ch, momentum, meanf, var, n);
 }
 
 __global__ void bn_eval_coeffs_kernel(const float *gamma, const float *beta, const float *rm, const float *rv, float eps,
@@ -215,6 +231,55 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const float *__restr
             if (relu) o = fmaxf(o, 0.f);
             a[e] = o;
             if (a_bf16) a_bf16[e] = __float2bfloat16_rn(o);
+        }
+    }
+}
+
+// Training-mode BatchNorm whose statistics arrive as per-channel sums from the producing convolution's epilogue: every
+// thread derives the coefficients of its four channels itself (grid x block is a multiple of C/4: a thread keeps its
+// channels over the grid stride), so the finalize launch between the convolution and this pass disappears; the first C/4
+// threads of block 0 also publish scale / shift / mean / rstd for the backward pass and update the running statistics.
+__global__ void __launch_bounds__(kThreads) bn_apply_sums_kernel(const float *__restrict__ y, long long total, int c, int n,
+                                                                 const double *__restrict__ sums, const float *__restrict__ gamma,
+                                                                 const float *__restrict__ beta, float eps, float momentum,
+                                                                 float *running_mean, float *running_var, float *scale_out,
+                                                                 float *shift_out, float *save_mean, float *save_rstd,
+                                                                 const float *__restrict__ residual, int relu, float *__restrict__ a,
+                                                                 __nv_bfloat16 *__restrict__ a_bf16) {
+    const long long tv = total >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int ch = (int)((e << 2) % c);
+    float sc[4], sh[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float meanf, rstd;
+        double var;
+        bn_coeffs(sums[ch + q], sums[c + ch + q], n, gamma ? gamma[ch + q] : 1.f, beta ? beta[ch + q] : 0.f, eps, sc[q], sh[q], meanf,
+                  rstd, var);
+        if (e < (c >> 2)) {          // block 0, one thread per group of four channels
+            scale_out[ch + q] = sc[q];
+            shift_out[ch + q] = sh[q];
+            if (save_mean) save_mean[ch + q] = meanf;
+            if (save_rstd) save_rstd[ch + q] = rstd;
+            bn_update_running(running_mean, running_var, ch + q, momentum, meanf, var, n);
+        }
+    }
+    for (; e < tv; e += stride) {
+        const float4 v = __ldg((const float4 *)y + e);
+        float4 o = make_float4(fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3]));
+        if (residual) {
+            const float4 r = __ldg((const float4 *)residual + e);
+            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        ((float4 *)a)[e] = o;
+        if (a_bf16) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+            uint2 pk;
+            pk.x = *(uint32_t *)&lo;
+            pk.y = *(uint32_t *)&hi;
+            ((uint2 *)a_bf16)[e] = pk;
         }
     }
 }
@@ -382,6 +447,32 @@ extern "C" int toda_bn_apply(const float *y, int n, int c, const float *scale, c
         bn_apply_kernel<true><<<grid_for(total / 4, per_sm_vec), kThreads, 0, st>>>(y, total, c, scale, shift, residual, relu, a, (__nv_bfloat16 *)a_bf16);
     else
         bn_apply_kernel<false><<<grid_for(total, per_sm_scalar), kThreads, 0, st>>>(y, total, c, scale, shift, residual, relu, a, (__nv_bfloat16 *)a_bf16);
+    TODA_LAUNCH_OK();
+    return TODA_OK;
+}
+
+extern "C" int toda_bn_apply_sums(const float *y, int n, int c, const double *sums, const float *gamma, const float *beta, float eps,
+                                  float momentum, float *running_mean, float *running_var, float *scale, float *shift,
+                                  float *save_mean, float *save_rstd, const float *residual, int relu, float *a, void *a_bf16,
+                                  void *stream) {
+    TODA_CHECK_ARG(n >= 0 && c > 0 && sums && scale && shift, "bn_apply_sums: bad args");
+    cudaStream_t st = (cudaStream_t)stream;
+    // the fused kernel needs a thread to keep its four channels over the grid stride; other shapes (none in these backbones)
+    // and empty inputs (the running statistics are still updated) take the two-launch route
+    if (n == 0 || c % 4 != 0 || kThreads % (c / 4) != 0) {
+        int rc = toda_bn_finalize_sums(sums, n, c, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, save_mean,
+                                       save_rstd, stream);
+        if (rc) return rc;
+        return toda_bn_apply(y, n, c, scale, shift, residual, relu, a, a_bf16, stream);
+    }
+    TODA_CHECK_ARG(y && a, "bn_apply_sums: null pointer");
+    const long long total = (long long)n * c;
+    static int per_sm = 0;
+    if (!per_sm) per_sm = resident_grid(bn_apply_sums_kernel, (int64_t)1 << 40) / kNumSMs;
+    const int64_t need = (total / 4 + kThreads - 1) / kThreads, cap = (int64_t)per_sm * kNumSMs;
+    const int grid = (int)(need < 1 ? 1 : (need < cap ? need : cap));
+    bn_apply_sums_kernel<<<grid, kThreads, 0, st>>>(y, total, c, n, sums, gamma, beta, eps, momentum, running_mean, running_var, scale,
+                                                    shift, save_mean, save_rstd, residual, relu, a, (__nv_bfloat16 *)a_bf16);
     TODA_LAUNCH_OK();
     return TODA_OK;
 }

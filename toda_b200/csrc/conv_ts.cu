@@ -52,11 +52,26 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+// A lost arrival must not hang the GPU box: a wait gives up (printf + trap) after kWaitLimitNs of wall-clock time.  The limit
+// is time-based and generous -- a spin count of a few tens of milliseconds fired in a 2-GPU run, where the first NCCL
+// all-reduce (communicator set-up, buffer registration) overlaps the backward pass and stalls every kernel on the device far
+// longer than any wait of this kernel lasts by itself.
+constexpr unsigned long long kWaitLimitNs = 4000000000ull;
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+    printf("conv_ts: mbarrier timeout smem=0x%x parity=%u block=%d warp=%d lane=%d\n", bar, parity, (int)blockIdx.x, (int)(threadIdx.x >> 5), (int)(threadIdx.x & 31));
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0, spins = 0;
+    unsigned long long t0 = 0;
     while (!done) {
         // (the last operand is the suspend-time hint in ns: the thread sleeps in hardware until the phase completes or the
-        // time is up, so a waiting role re-issues a handful of instructions per 16 us instead of spinning next to the
+        // time is up, so a waiting role re-issues a handful of instructions per wake-up instead of spinning next to the
         // gather warps it shares a scheduler with; an arrival wakes it at once)
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -65,9 +80,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity), "r"(0x4000u)
             : "memory");
-        if (!done && ++spins > (1u << 20)) {           // a lost arrival must not hang the GPU box
-            printf("conv_ts: mbarrier timeout smem=0x%x parity=%u block=%d warp=%d lane=%d\n", bar, parity, (int)blockIdx.x, (int)(threadIdx.x >> 5), (int)(threadIdx.x & 31));
-            __trap();
+        if (!done && (++spins & 0xfffu) == 0u) {
+            const unsigned long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > kWaitLimitNs) mbar_timeout(bar, parity);
         }
     }
 }
@@ -75,6 +91,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // takes issue slots from the gather warp it shares a scheduler with (the epilogue's wait alone was 12 % of all instructions)
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
     uint32_t done = 0, spins = 0;
+    unsigned long long t0 = 0;
     while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -85,9 +102,10 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
             : "memory");
         if (done) break;
         __nanosleep(256);
-        if (++spins > (1u << 18)) {
-            printf("conv_ts: mbarrier timeout (relaxed) smem=0x%x parity=%u block=%d warp=%d\n", bar, parity, (int)blockIdx.x, (int)(threadIdx.x >> 5));
-            __trap();
+        if ((++spins & 0xfffu) == 0u) {
+            const unsigned long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > kWaitLimitNs) mbar_timeout(bar, parity);
         }
     }
 }
@@ -472,17 +490,21 @@ __global__ void __launch_bounds__((TsCfg<CIN, COUT>::kThreads), 1) conv_ts_fwd_k
                 load_li(kbA, true, liA);
                 load_li(kbB, two, liB);
                 const uint32_t k_first = CIN == 128 ? (kbA >> 1) : kbA * PARTS;
-                release_below((k_first >= ugs ? 1u : 0u) + (k_first >= ugs2 ? 1u : 0u));   // slabs of earlier groups are no longer read by this warp
+                const uint32_t g_first = (k_first >= ugs ? 1u : 0u) + (k_first >= ugs2 ? 1u : 0u);
+                const uint32_t kb_last = two ? kbB : kbA;
+                const uint32_t k_last = min(CIN == 128 ? (kb_last >> 1) : kb_last * PARTS + PARTS - 1, ukvol - 1u);
+                const uint32_t g_last = (k_last >= ugs ? 1u : 0u) + (k_last >= ugs2 ? 1u : 0u);
+                release_below(g_first);                 // slabs of earlier groups are no longer read by this warp
                 TS_DBG((tid & 127) == 0, 1, gA);
-                {
-                    const uint32_t kb_last = two ? kbB : kbA;
-                    const uint32_t k_last = min(CIN == 128 ? (kb_last >> 1) : kb_last * PARTS + PARTS - 1, ukvol - 1u);
-                    wait_group((k_last >= ugs ? 1u : 0u) + (k_last >= ugs2 ? 1u : 0u));
-                }
+                // With two slab buffers (256-byte rows) groups 0 and 2 of a tile share a buffer: a pair whose blocks lie in
+                // those two groups (group 1 fully masked out) cannot have both resident -- it is walked one block at a time,
+                // the first group handed back in between.  (Waiting for both deadlocked the CTA on such a tile.)
+                const bool apart = NB < 3 && g_last >= g_first + (uint32_t)NB;
+                wait_group(apart ? g_first : g_last);
                 // (the A slot is waited for while the loads are in flight: the barrier probe overlaps them)
                 uint32_t va[32];
                 bool fixA = load_data(kbA, liA, va);
-                if (C::kBoth) {
+                if (C::kBoth && !apart) {
                     uint32_t vb[32];
                     bool fixB = load_data(kbB, liB, vb);
                     if (gp >= (uint32_t)kASlots) {      // the pair that used this slot before (gp - kASlots) has been consumed
@@ -509,6 +531,10 @@ __global__ void __launch_bounds__((TsCfg<CIN, COUT>::kThreads), 1) conv_ts_fwd_k
                     __syncwarp();
                     TS_STTM_X32(t_lane + aslot * 64u, va);
                     if (two) {                          // (the table entries of block B were fetched with those of block A)
+                        if (apart) {
+                            release_below(g_last);
+                            wait_group(g_last);
+                        }
                         fixA = load_data(kbB, liB, va);
                         if (__any_sync(0xffffffffu, fixA)) fix_block(kbB, liB, va);
                         __syncwarp();

@@ -16,10 +16,10 @@ extern "C" int toda_layer_fwd(const toda_layer_fwd_args *p, void *stream) {
                                   tc ? p->sums : nullptr, p->w_bf16, p->precision, p->conv_ws, p->conv_ws_bytes, stream);
     if (rc) return rc;
     if (n == 0) return TODA_OK;
-    if (tc)
-        rc = toda_bn_finalize_sums(p->sums, n, c, p->gamma, p->beta, p->eps, p->momentum, p->running_mean, p->running_var, scale, shift,
-                                   mean, rstd, stream);
-    else if (p->training)
+    if (tc)   // statistics from the convolution's epilogue: coefficients and apply in one launch
+        return toda_bn_apply_sums(p->y, n, c, p->sums, p->gamma, p->beta, p->eps, p->momentum, p->running_mean, p->running_var, scale,
+                                  shift, mean, rstd, p->residual, p->relu, p->a, p->a_bf16, stream);
+    if (p->training)
         rc = toda_bn_stats(p->y, n, c, p->gamma, p->beta, p->eps, p->momentum, p->running_mean, p->running_var, scale, shift, mean, rstd,
                            p->bn_ws, p->bn_ws_bytes, stream);
     else

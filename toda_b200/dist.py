@@ -42,6 +42,7 @@ class FlatGradBucket:
             for i in range(lo, hi):
                 self._bucket_of[i] = b
         self._overlap = bool(overlap)
+        self._sync = True            # False inside no_sync(): backward passes stay local
         self._hooks = []
         if self._overlap and hasattr(p0, "register_post_accumulate_grad_hook"):
             for p in self.params:
@@ -65,8 +66,22 @@ class FlatGradBucket:
             p.grad = None
         self._reset()
 
+    def no_sync(self):
+        """Context manager (the counterpart of DistributedDataParallel.no_sync): backward passes inside it launch no
+        collective -- for a pass that only some ranks run (per-kernel profiling on rank 0) or for gradient accumulation."""
+        bucket = self
+
+        class _NoSync:
+            def __enter__(self):
+                self.prev, bucket._sync = bucket._sync, False
+
+            def __exit__(self, *exc):
+                bucket._sync = self.prev
+                return False
+        return _NoSync()
+
     def _on_grad(self, p):
-        if self._world() == 1:
+        if not self._sync or self._world() == 1:
             return
         i = self._index.get(id(p))
         if i is None:
@@ -106,7 +121,7 @@ class FlatGradBucket:
         got no gradient on this rank), waits, and points every p.grad at its averaged view of the flat buffer (also for
         parameters whose grad was None here: the other ranks' contributions must reach this replica too)."""
         world = self._world()
-        if world == 1:
+        if world == 1 or not self._sync:
             return
         for b in range(self._next, len(self.buckets)):
             self._launch(b)

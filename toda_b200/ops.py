@@ -888,7 +888,7 @@ def _layer_forward(x, x_bf16, weight, bias, rb, precision, gamma, beta, running_
         gamma.data_ptr(), beta.data_ptr(), float(eps), float(momentum), _vp(running_mean), _vp(running_var), int(bool(training)),
         _vp(res), int(bool(relu)), y.data_ptr(), sp + 16 * cout, sp, a.data_ptr(), _vp(ab), bws.data_ptr(), bws.numel())
     _C.check(L.toda_layer_fwd(ctypes.byref(args), _stream()), "toda_layer_fwd")
-    _count(3 if tc else 4)
+    _count(2 if (tc and training and n_out > 0) else (3 if tc else 4))
     mean = small[2 * cout:3 * cout] if training else running_mean
     rstd = small[3 * cout:4 * cout] if training else None
     return a, ab, (x, x_bf16, weight, y, a, gamma, mean, rstd)
