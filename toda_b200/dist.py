@@ -9,6 +9,8 @@ all-reduced (NCCL AVG, asynchronously, on NCCL's own stream) as soon as its last
 collective overlaps the dgrad / wgrad kernels of the earlier layers.  Afterwards every p.grad IS a view of the flat
 buffer: no unpack copy, no division kernel.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -21,7 +23,9 @@ def shard_frames(global_first_frame, frames_per_rank, rank):
 class FlatGradBucket:
     """Usage per step:  bucket.zero(); loss.backward(); bucket.all_reduce_mean()."""
 
-    def __init__(self, params, bucket_bytes=3 << 20, overlap=True, group=None):
+    def __init__(self, params, bucket_bytes=3 << 20, overlap=None, group=None):
+        if overlap is None:         # TODA_DIST_OVERLAP=0: one all-reduce after the backward pass (A/B measurements)
+            overlap = os.environ.get("TODA_DIST_OVERLAP", "1") != "0"
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         p0 = self.params[0]
