@@ -39,6 +39,7 @@ constexpr uint32_t kLidxGlobal = 0xFFFEu;         // neighbour exists but is not
 // Same bytes in flight per SM either way; the second is ahead for 256-byte rows, the first for the narrow layers.
 // the warp scheduler favours high warp ids: the latency-critical gather warps get them
 constexpr int kWarpMma = 4, kWarpLoader = 5, kWarpB = 6, kWarpLoader2 = 7, kWarpGather0 = 8;
+constexpr int kLoaders = 2;   // slab loader warps (2: even / odd blocks)
 // A ring: pair slots of 2 x 32 TMEM columns (2 x 64 K elements) behind the two accumulators
 // Pair gp is produced by warpgroup gp % 4 into slot gp % kSlots.  Its barriers are NOT per slot but per pair index modulo
 // 16 (a_full / a_empty[gp & 15]): every barrier is then waited on by one warpgroup only, which sees each of its phases in turn
@@ -57,6 +58,12 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 // (communicator set-up, buffer registration) overlaps the backward pass and stalls every kernel on the device far longer
 // than any wait of this kernel lasts by itself.  (A wall-clock limit read from %globaltimer cost registers in every inlined
 // wait and 10 % of the kernel's speed; the printf that names the barrier is compiled in with -DTODA_TS_VERBOSE_TIMEOUT.)
+#ifdef TODA_TS_VERBOSE_TIMEOUT
+__shared__ int ts_prog[32];
+#define TS_PROG(v) do { } while (0)
+#else
+#define TS_PROG(v) do { } while (0)
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0, spins = 0;
     while (!done) {
@@ -72,7 +79,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
         if (!done && ++spins > (1u << 26)) {
 #ifdef TODA_TS_VERBOSE_TIMEOUT
-            printf("conv_ts: mbarrier timeout smem=0x%x parity=%u block=%d warp=%d lane=%d\n", bar, parity, (int)blockIdx.x, (int)(threadIdx.x >> 5), (int)(threadIdx.x & 31));
+            if ((threadIdx.x & 31) == 0) {
+                volatile int *pg = ts_prog;
+                printf("conv_ts: mbarrier timeout smem=0x%x parity=%u block=%d warp=%d | prog mma %x L0 %x L1 %x B %x g8 %x g12 %x g16 %x g20 %x me %x\n", bar, parity, (int)blockIdx.x,
+                       (int)(threadIdx.x >> 5), pg[4], pg[5], pg[7], pg[6], pg[8], pg[12], pg[16], pg[20], pg[threadIdx.x >> 5]);
+            }
+            if (spins < (1u << 22) + (1u << 21)) { spins += (1u << 20); continue; }
 #endif
             __trap();
         }
@@ -322,7 +334,7 @@ __global__ void __launch_bounds__((TsCfg<CIN, COUT>::kThreads), 1) conv_ts_fwd_k
             mbar_init(lidx_empty + 8 * b, C::kGatherWarps);
         }
         for (int b = 0; b < NB; ++b) {
-            mbar_init(slab_full + 8 * b, 1);       // arrive.expect_tx by the loader; the TMA box copies complete the bytes
+            mbar_init(slab_full + 8 * b, 1);       // arrive.expect_tx by the first loader warp; the TMA box copies complete the bytes
             mbar_init(slab_empty + 8 * b, C::kGatherWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -370,6 +382,7 @@ __global__ void __launch_bounds__((TsCfg<CIN, COUT>::kThreads), 1) conv_ts_fwd_k
             mbar_wait(lidx_full + 8 * ib, (it >> 1) & 1u);
             TS_DBG(tid == 256, 23, it);
             const uint32_t lidx_tile = lidx_base + ib * kLidxBytes + 2u * row;
+            TS_PROG((int)((it << 12) | (uq << 4) | ur));
             // slab buffer, barrier offset and phase parity of the tile's (up to three) offset groups
             uint32_t sbuf[3], sbar[3], spar[3];
 #pragma unroll
@@ -649,6 +662,7 @@ __global__ void __launch_bounds__((TsCfg<CIN, COUT>::kThreads), 1) conv_ts_fwd_k
                     m32 &= m32 - 1u;
                 }
                 const int aslot = gp % kASlots;
+                TS_PROG((it << 12) | gp);
                 mbar_wait(a_full + 8 * (gp & (kABars - 1)), (gp / kABars) & 1);
                 if (!BRES) {
                     mbar_wait(b_full + 8 * (gA % SB), (gA / SB) & 1);
@@ -684,7 +698,7 @@ __global__ void __launch_bounds__((TsCfg<CIN, COUT>::kThreads), 1) conv_ts_fwd_k
             if (elect_one()) umma_commit(acc_full + 8 * ab);
             __syncwarp();
         }
-    } else if (warp == kWarpLoader || warp == kWarpLoader2) {
+    } else if (warp == kWarpLoader || (warp == kWarpLoader2 && kLoaders == 2)) {
         // ------------------------------------------------------------------ loaders (two warps: even / odd blocks; issuing a TMA costs
         // ~65 cycles): table slice + row slabs, up to NB groups ahead.
         // One TMA box copy (16 rows, hardware-swizzled) per cached block, lane i issuing block i of the unit.  The block list of
@@ -701,6 +715,7 @@ __global__ void __launch_bounds__((TsCfg<CIN, COUT>::kThreads), 1) conv_ts_fwd_k
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int ib = it & 1;
+            TS_PROG((it << 4) | 5);
             if (L == 0 && lane == 0 && !(xmode & 64)) {
                 if (it >= 2) mbar_wait(lidx_empty + 8 * ib, ((it >> 1) - 1) & 1);
                 const uint32_t bytes = (uint32_t)kvol * (kTileM * 2);
@@ -710,27 +725,39 @@ __global__ void __launch_bounds__((TsCfg<CIN, COUT>::kThreads), 1) conv_ts_fwd_k
             __syncwarp();
             for (int grp = 0; grp < ngroups && !(xmode & 32); ++grp) {
                 const int u = it * ngroups + grp, buf = u % NB, use = u / NB;
+                TS_PROG((u << 4) | 1);
                 TS_DBG(L == 0 && lane == 0, 7, u);
                 const int bid = bid_n, nb = nb_n;
                 if (grp + 1 < ngroups) fetch_unit(t, grp + 1);
                 else fetch_unit(t + gridDim.x, 0);
-                if (use > 0) mbar_wait(slab_empty + 8 * buf, (use - 1) & 1);
-                TS_DBG(L == 0 && lane == 0, 8, u);
-                if (L == 0 && lane == 0) {
-                    if (nb > 0 && !(xmode & 8)) mbar_arrive_expect_tx(slab_full + 8 * buf, (uint32_t)nb * 16u * C::kRowBytes);
-                    else mbar_arrive(slab_full + 8 * buf);
+                // Only the first loader warp talks to the slab barriers; the second follows it unit by unit through a named
+                // hardware barrier.  (When both warps waited on slab_empty themselves, a unit in which the second warp had no
+                // block to fetch completed without it; that warp could then fall two uses of a buffer behind, where its
+                // parity wait never passes again: a deadlock seen a few times in ten runs on one rank's frames.)
+                if (L == 0) {
+                    if (use > 0) mbar_wait(slab_empty + 8 * buf, (use - 1) & 1);
+                    if (lane == 0) {
+                        if (nb > 0 && !(xmode & 8)) mbar_arrive_expect_tx(slab_full + 8 * buf, (uint32_t)nb * 16u * C::kRowBytes);
+                        else mbar_arrive(slab_full + 8 * buf);
+                    }
                 }
+                TS_PROG((u << 4) | 2);
+                TS_DBG(L == 0 && lane == 0, 8, u);
                 __syncwarp();
-                if (bid >= 0 && (lane & 1) == L && !(xmode & 8)) {
+                if (kLoaders == 2) asm volatile("barrier.sync 1, 64;" ::: "memory");
+                if (bid >= 0 && (kLoaders == 1 || (lane & 1) == L) && !(xmode & 8)) {
                     const uint32_t dst = slab_base + buf * C::kSlab + lane * (16 * C::kRB);
 #pragma unroll
                     for (int h = 0; h < C::kHalves; ++h)
                         tma_load_2d(dst + h * C::kHalfSlab, &map_x, h * 64, bid * 16, slab_full + 8 * buf);
                 }
+                TS_PROG((u << 4) | 3);
                 TS_DBG(L == 0 && lane == 0, 9, u);
             }
+            TS_PROG((it << 4) | 4);
         }
-    } else {
+        TS_PROG(0xfffff);
+    } else if (warp == kWarpB) {
         // ------------------------------------------------------------------ weight producer (the warp walks the tiles together: the
         // K-block mask is a warp-collective; lane 0 issues the TMA copies)
         if (BRES) {
