@@ -186,6 +186,8 @@ size_t toda_spconv_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol, in
  * (the FFMA kernel tests this per tile itself). */
 int toda_table_tile_masks(const int32_t *nbr, int n_out, int kvol, uint32_t *masks, void *stream);
 int toda_spconv_uses_tensor_cores(int cin, int cout, int kvol, int precision);
+/* the same question for toda_spconv_wgrad */
+int toda_spconv_wgrad_uses_tensor_cores(int cin, int cout, int kvol, int precision);
 int toda_spconv_fwd(const float *x, const void *x_bf16, int n_in, int cin, const int32_t *nbr, int n_out, int kvol,
                     const float *w, int cout, const float *bias, float *y, const int32_t *out_rows,
                     const uint32_t *tile_masks, double *bn_sums, int precision, void *workspace, size_t workspace_bytes,

@@ -118,3 +118,39 @@ def test_backbone_step_with_plans_is_bit_identical():
     for k in a["grads"]:
         # (BatchNorm sums are fp64 atomics in both paths: order-dependent in the last bits)
         np.testing.assert_allclose(a["grads"][k], b["grads"][k], rtol=1e-5, atol=1e-7, err_msg=k)
+
+
+def test_strided_forward_stress_on_second_rank_frames():
+    """Regression guard for a deadlock of the row-cache kernel that showed only on the frames the SECOND rank of a
+    multi-GPU run gets (synthetic frames 12-15), and only a few times in ten 20-step runs: on the 32->64 stride-2 forward
+    conv the second slab-loader warp waited on slab_empty by itself, fell two uses of a buffer behind in units where it had
+    no block to fetch, and its parity wait never passed again.  (It now follows the first loader through a named
+    barrier.)  The test repeats that layer 400 times on those frames and checks every launch against the first."""
+    from toda_b200 import ops, synth
+    cfg = synth.CONFIGS["nus_0075"]
+    frames, collated = synth.make_batch("nus_0075", 4, first_frame=12)
+    dev = torch.device(DEV, 0)
+    offs = torch.from_numpy(np.cumsum([0] + [f.shape[0] for f in frames]).astype(np.int32)).to(dev)
+    grid = synth.grid_size_xyz(cfg["pc_range"], cfg["voxel_size"])
+    _, coords, _, _ = ops.voxelize(torch.from_numpy(collated).to(dev), offs, cfg["pc_range"], cfg["voxel_size"], 10, 120000, xyz_col=1,
+                                   feat_col=1, num_features=5, order=ops.ORDER_CANONICAL, grid=grid)
+    shape = [int(grid[2]) + 1, int(grid[1]), int(grid[0])]
+    index = ops.OccupancyIndex(4, shape, dev, "stress")
+    index.insert(coords)
+    index.build(coords.shape[0], known_n=coords.shape[0])
+    _, index = ops.rulebook_sparse(index, [3, 3, 3], [2, 2, 2], [1, 1, 1], ("stress", 1), cin=16, cout=32)
+    rb, index3 = ops.rulebook_sparse(index, [3, 3, 3], [2, 2, 2], [1, 1, 1], ("stress", 2), cin=32, cout=64)
+    assert rb.plan is not None
+    x = torch.randn(rb.n_in, 32, device=dev)
+    xb = x.to(torch.bfloat16)
+    w = torch.randn(27, 32, 64, device=dev) * 0.1
+    ref = None
+    for i in range(400):
+        y = ops._conv_call(x, xb, 32, rb.nbr_fwd, rb.n_out, 27, w, 64, None, ops.CONV_BF16, tile_masks=rb.tile_masks, plan=rb.plan)
+        if i % 50 == 0:
+            torch.cuda.synchronize()
+            if ref is None:
+                ref = y.clone()
+            assert torch.equal(y, ref)
+    torch.cuda.synchronize()
+    index3.release()

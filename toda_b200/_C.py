@@ -38,6 +38,7 @@ SIGNATURES = {
     "toda_weight_repack": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "toda_spconv_fwd_workspace_bytes": (c_sz, [c_int] * 5),
     "toda_spconv_uses_tensor_cores": (c_int, [c_int] * 4),
+    "toda_spconv_wgrad_uses_tensor_cores": (c_int, [c_int] * 4),
     "toda_parity_order_workspace_bytes": (c_sz, [c_int]),
     "toda_parity_order": (c_int, [c_vp, c_int, _IP, _IP, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "toda_table_tile_masks": (c_int, [c_vp, c_int, c_int, c_vp, c_vp]),

@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float *__r
             o.y = fmaf(A[1], g4.y, fmaf(B[1], y4.y, C[1]));
             o.z = fmaf(A[2], g4.z, fmaf(B[2], y4.z, C[2]));
             o.w = fmaf(A[3], g4.w, fmaf(B[3], y4.w, C[3]));
-            ((float4 *)dy)[e] = o;
+            if (dy) ((float4 *)dy)[e] = o;
             if (dy_bf16) {
                 __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
                 uint2 pk;
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float *__r
             } else {
                 o = gm * rs * g;
             }
-            dy[e] = o;
+            if (dy) dy[e] = o;
             if (dy_bf16) dy_bf16[e] = __float2bfloat16_rn(o);
         }
     }
@@ -481,7 +481,9 @@ extern "C" int toda_bn_bwd(const float *da, const float *a, const float *y, int 
                            const float *save_mean, const float *save_rstd, int relu, int training, float *dy, void *dy_bf16,
                            float *dresidual, float *dgamma, float *dbeta, void *workspace, size_t workspace_bytes, void *stream) {
     TODA_CHECK_ARG(n >= 0 && c > 0 && c <= 256, "bn_bwd: unsupported sizes n=%d c=%d", n, c);
-    TODA_CHECK_ARG(save_mean && save_rstd && workspace && (n == 0 || (da && y && dy)) && (!relu || a || n == 0),
+    // dy may be NULL when dy_bf16 is given: the fp32 gradient is then not stored (a caller whose consumers -- tensor-core
+    // dgrad and wgrad -- only read the bf16 copy saves 4 of the ~30 bytes per element this pass moves)
+    TODA_CHECK_ARG(save_mean && save_rstd && workspace && (n == 0 || (da && y && (dy || dy_bf16))) && (!relu || a || n == 0),
                    "bn_bwd: null pointer");
     if (workspace_bytes < bn_ws_bytes(c)) { toda_set_error("bn_bwd: workspace too small"); return TODA_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;

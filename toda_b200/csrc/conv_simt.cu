@@ -267,6 +267,10 @@ extern "C" int toda_spconv_uses_tensor_cores(int cin, int cout, int kvol, int pr
     return (precision == TODA_CONV_BF16 || precision == TODA_CONV_BF16X3) && conv_tc_supported(cin, cout, kvol) ? 1 : 0;
 }
 
+extern "C" int toda_spconv_wgrad_uses_tensor_cores(int cin, int cout, int kvol, int precision) {
+    return (precision == TODA_CONV_BF16 || precision == TODA_CONV_BF16X3) && conv_tc_wgrad_supported(cin, cout, kvol) ? 1 : 0;
+}
+
 extern "C" size_t toda_spconv_fwd_workspace_bytes(int n_in, int cin, int cout, int kvol, int precision) {
     if (precision == TODA_CONV_BF16 && n_in >= 0 && cin > 0 && cout > 0 && kvol > 0 && conv_tc_supported(cin, cout, kvol))
         return conv_tc_fwd_workspace_bytes(n_in, cin, cout, kvol);

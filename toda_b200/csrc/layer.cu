@@ -44,8 +44,13 @@ extern "C" int toda_layer_bwd(const toda_layer_bwd_args *p, void *stream) {
         }
         return TODA_OK;
     }
-    int rc = toda_bn_bwd(p->da, p->a_mask, p->y, n, c, p->gamma, p->mean, p->rstd, p->relu, p->training, p->dy, p->dy_bf16, p->dres,
-                         p->dgamma, p->dbeta, p->bn_ws, p->bn_ws_bytes, stream);
+    // The fp32 copy of the gradient between BatchNorm and the convolution is only written when something reads it: the
+    // tensor-core dgrad / wgrad take the bf16 copy the same pass writes (4 of ~30 bytes per element of this HBM-bound pass).
+    const bool dy_f32_read = p->need_db || !p->dy_bf16 || p->precision != TODA_CONV_BF16 ||
+                             (p->need_dx && !toda_spconv_uses_tensor_cores(c, p->cin, p->kvol, p->precision)) ||
+                             (p->need_dw && !toda_spconv_wgrad_uses_tensor_cores(p->cin, c, p->kvol, p->precision));
+    int rc = toda_bn_bwd(p->da, p->a_mask, p->y, n, c, p->gamma, p->mean, p->rstd, p->relu, p->training, dy_f32_read ? p->dy : nullptr,
+                         p->dy_bf16, p->dres, p->dgamma, p->dbeta, p->bn_ws, p->bn_ws_bytes, stream);
     if (rc) return rc;
     if (p->need_dx) {
         // dgrad = the forward kernel on the input-stationary table with transposed (SubM: mirrored) weights; `addend` is the
