@@ -481,10 +481,10 @@ def roofline_from_profile(prof, bd, peaks, step_ms):
                 row["frac_of_hbm_peak"] = round(row["gbs"] / peaks["hbm_gbs"], 4)
         layers.append(row)
     # dominant KERNEL (device function): forward and dgrad convolutions are the same tcgen05 kernel
-    # (conv_tc_fwd_kernel / conv_tma_fwd_kernel), the weight gradient is conv_tc_wgrad_kernel
+    # (conv_ts_fwd_kernel, csrc/conv_ts.cu), the weight gradient is conv_tc_wgrad_kernel
     fams = defaultdict(lambda: dict(ms=0.0, calls=0, flops=0.0, bytes=0.0, kind="hbm"))
     for key, g in groups.items():
-        fam = ("conv_tc_fwd_kernel (fwd + dgrad, all layers)" if key.startswith(("conv_fwd", "conv_dgrad")) else
+        fam = ("conv_ts_fwd_kernel (fwd + dgrad, all layers)" if key.startswith(("conv_fwd", "conv_dgrad")) else
                "conv_tc_wgrad_kernel (all layers)" if key.startswith("conv_wgrad") else key)
         f = fams[fam]
         for k in ("ms", "calls", "flops", "bytes"):
@@ -492,7 +492,7 @@ def roofline_from_profile(prof, bd, peaks, step_ms):
         f["kind"] = g.get("kind", "hbm")
     top_key, top = max(fams.items(), key=lambda kv: kv[1]["ms"])
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")      # dram bytes per launch from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")      # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(top_key.split(" ")[0])
     if top.get("kind") == "conv":
