@@ -402,7 +402,8 @@ def run_ours(args, rank, world, local_rank):
     line = dict(metric=WORKLOADS[WORKLOAD]["metric"], value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype={"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16x3 (split bf16, fp32-class)"}[args.precision], data="synthetic",
-                config=dict(workload=WORKLOADS[WORKLOAD]["desc"], workload_key=WORKLOAD,
+                config=dict(conv_kernel="row-cache / TMEM-operand (conv_ts.cu, opt-in)" if ops.tile_plans_enabled() else "round-1 tcgen05 kernels (conv_tc.cu / conv_tma.cu)",
+                            workload=WORKLOADS[WORKLOAD]["desc"], workload_key=WORKLOAD,
                             frames_per_gpu=FRAMES_PER_GPU, points_per_frame=int(hosts[0][0].shape[0] / FRAMES_PER_GPU),
                             voxels_per_frame=int(bd["voxel_coords"].shape[0] / FRAMES_PER_GPU), conv_precision=args.precision,
                             l2="inputs rotate over %d pre-staged batches and each step streams >1 GB of activations (>> 126 MB L2)" % POOL,
@@ -482,9 +483,11 @@ def roofline_from_profile(prof, bd, peaks, step_ms):
         layers.append(row)
     # dominant KERNEL (device function): forward and dgrad convolutions are the same tcgen05 kernel
     # (conv_ts_fwd_kernel, csrc/conv_ts.cu), the weight gradient is conv_tc_wgrad_kernel
+    from toda_b200 import ops as _ops
+    fwd_kernel = "conv_ts_fwd_kernel" if _ops.tile_plans_enabled() else "conv_tc_fwd_kernel"
     fams = defaultdict(lambda: dict(ms=0.0, calls=0, flops=0.0, bytes=0.0, kind="hbm"))
     for key, g in groups.items():
-        fam = ("conv_ts_fwd_kernel (fwd + dgrad, all layers)" if key.startswith(("conv_fwd", "conv_dgrad")) else
+        fam = (fwd_kernel + " (fwd + dgrad, all layers)" if key.startswith(("conv_fwd", "conv_dgrad")) else
                "conv_tc_wgrad_kernel (all layers)" if key.startswith("conv_wgrad") else key)
         f = fams[fam]
         for k in ("ms", "calls", "flops", "bytes"):
@@ -492,9 +495,11 @@ def roofline_from_profile(prof, bd, peaks, step_ms):
         f["kind"] = g.get("kind", "hbm")
     top_key, top = max(fams.items(), key=lambda kv: kv[1]["ms"])
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")      # dram bytes per launch from the committed ncu --set full capture
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(top_key.split(" ")[0])
+    # dram bytes per launch from the committed ncu --set full captures (r02: conv_ts_fwd_kernel + wgrad; r01: conv_tc_fwd_kernel)
+    for tname in ("r02_traffic.json", "r01_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if traffic is None and os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(top_key.split(" ")[0])
     if top.get("kind") == "conv":
         achieved = top["flops"] / (top["ms"] * 1e-3) / 1e12
         roof = dict(bound="tensor", kernel=top_key, achieved=achieved, peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s",

@@ -35,11 +35,12 @@ def test_plan_kernel_matches_round1_kernel_subm(n, cin, cout):
     index = ops.OccupancyIndex(batch, shape, torch.device(DEV, 0), "ts")
     index.insert(torch.from_numpy(idx).to(DEV))
     index.build(n)
+    prev = ops.tile_plans_enabled()
     ops.set_tile_plans(True)
     try:
         rb = ops.rulebook_subm(index, [3, 3, 3], channels=max(cin, cout))
     finally:
-        ops.set_tile_plans(True)
+        ops.set_tile_plans(prev)
     assert rb.plan is not None
     x = torch.from_numpy(feats).to(DEV)
     w = torch.randn(27, cin, cout, device=DEV) * 0.1
@@ -89,7 +90,7 @@ def test_plan_kernel_full_size_chain_all_geometries():
                 (ya, _), (yb, _) = _both(dy, cout, rb.nbr_bwd, rb.n_in, kvol, wt, cin, rb.dgrad_plan, None)
             assert torch.equal(ya, yb), ("down dgrad", cin, cout)
     finally:
-        ops.set_tile_plans(True)
+        ops.set_tile_plans(False)
 
 
 def test_backbone_step_with_plans_is_bit_identical():
@@ -110,7 +111,7 @@ def test_backbone_step_with_plans_is_bit_identical():
             _, net = PU.build_pair("VoxelResBackBone8x", 5, g["grid_size"], seed=int(g["seed"]))
             res.append(PU.run_backbone(net, hc, vf, vc, 2, cot=cot, train=True))
     finally:
-        ops.set_tile_plans(True)
+        ops.set_tile_plans(False)
         G.set_conv_precision("fp32")
     a, b = res
     assert np.array_equal(a["spatial_features"], b["spatial_features"])
@@ -125,7 +126,8 @@ def test_strided_forward_stress_on_second_rank_frames():
     multi-GPU run gets (synthetic frames 12-15), and only a few times in ten 20-step runs: on the 32->64 stride-2 forward
     conv the second slab-loader warp waited on slab_empty by itself, fell two uses of a buffer behind in units where it had
     no block to fetch, and its parity wait never passed again.  (It now follows the first loader through a named
-    barrier.)  The test repeats that layer 400 times on those frames and checks every launch against the first."""
+    barrier.)  The test repeats that layer 400 times on those frames and checks every launch against the first.  (The
+    kernel stays opt-in: a second, rarer hang of the same family was still open at the end of round 2, see ops.py.)"""
     from toda_b200 import ops, synth
     cfg = synth.CONFIGS["nus_0075"]
     frames, collated = synth.make_batch("nus_0075", 4, first_frame=12)
@@ -138,8 +140,12 @@ def test_strided_forward_stress_on_second_rank_frames():
     index = ops.OccupancyIndex(4, shape, dev, "stress")
     index.insert(coords)
     index.build(coords.shape[0], known_n=coords.shape[0])
-    _, index = ops.rulebook_sparse(index, [3, 3, 3], [2, 2, 2], [1, 1, 1], ("stress", 1), cin=16, cout=32)
-    rb, index3 = ops.rulebook_sparse(index, [3, 3, 3], [2, 2, 2], [1, 1, 1], ("stress", 2), cin=32, cout=64)
+    ops.set_tile_plans(True)
+    try:
+        _, index = ops.rulebook_sparse(index, [3, 3, 3], [2, 2, 2], [1, 1, 1], ("stress", 1), cin=16, cout=32)
+        rb, index3 = ops.rulebook_sparse(index, [3, 3, 3], [2, 2, 2], [1, 1, 1], ("stress", 2), cin=32, cout=64)
+    finally:
+        ops.set_tile_plans(False)
     assert rb.plan is not None
     x = torch.randn(rb.n_in, 32, device=dev)
     xb = x.to(torch.bfloat16)

@@ -53,7 +53,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-// A lost arrival must not hang the GPU box: a wait gives up (printf + trap) after ~2^26 probes, i.e. seconds.  The limit is
+// A lost arrival must not hang the GPU box: a wait gives up (trap) after 2^22 probes (measured ~1.5 us per probe once nothing
+// moves any more: several seconds).  The limit is
 // deliberately generous -- one of a few tens of milliseconds fired in a 2-GPU run, where the first NCCL all-reduce
 // (communicator set-up, buffer registration) overlaps the backward pass and stalls every kernel on the device far longer
 // than any wait of this kernel lasts by itself.  (A wall-clock limit read from %globaltimer cost registers in every inlined
@@ -77,7 +78,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity), "r"(0x4000u)
             : "memory");
-        if (!done && ++spins > (1u << 26)) {
+        if (!done && ++spins > (1u << 22)) {
 #ifdef TODA_TS_VERBOSE_TIMEOUT
             if ((threadIdx.x & 31) == 0) {
                 volatile int *pg = ts_prog;
@@ -104,7 +105,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
             : "memory");
         if (done) break;
         __nanosleep(256);
-        if (++spins > (1u << 25)) {
+        if (++spins > (1u << 22)) {
 #ifdef TODA_TS_VERBOSE_TIMEOUT
             printf("conv_ts: mbarrier timeout (relaxed) smem=0x%x parity=%u block=%d warp=%d\n", bar, parity, (int)blockIdx.x, (int)(threadIdx.x >> 5));
 #endif
@@ -704,6 +705,7 @@ __global__ void __launch_bounds__((TsCfg<CIN, COUT>::kThreads), 1) conv_ts_fwd_k
         // One TMA box copy (16 rows, hardware-swizzled) per cached block, lane i issuing block i of the unit.  The block list of
         // unit u+1 is fetched while unit u is issued (a list read is two dependent L2 round trips).
         const int L = warp == kWarpLoader ? 0 : 1;
+        const bool idle_loader = L == 1 && (xmode & 256);   // TODA_TS_LOADERS=1: the first loader warp fetches every block
         int bid_n = -1, nb_n = 0;
         auto fetch_unit = [&](int t, int grp) {
             if (t < num_tiles) {
@@ -713,7 +715,7 @@ __global__ void __launch_bounds__((TsCfg<CIN, COUT>::kThreads), 1) conv_ts_fwd_k
         };
         fetch_unit(blockIdx.x, 0);
         int it = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        for (int t = blockIdx.x; t < num_tiles && !idle_loader; t += gridDim.x, ++it) {
             const int ib = it & 1;
             TS_PROG((it << 4) | 5);
             if (L == 0 && lane == 0 && !(xmode & 64)) {
@@ -744,8 +746,8 @@ __global__ void __launch_bounds__((TsCfg<CIN, COUT>::kThreads), 1) conv_ts_fwd_k
                 TS_PROG((u << 4) | 2);
                 TS_DBG(L == 0 && lane == 0, 8, u);
                 __syncwarp();
-                if (kLoaders == 2) asm volatile("barrier.sync 1, 64;" ::: "memory");
-                if (bid >= 0 && (kLoaders == 1 || (lane & 1) == L) && !(xmode & 8)) {
+                if (kLoaders == 2 && !(xmode & 256)) asm volatile("barrier.sync 1, 64;" ::: "memory");
+                if (bid >= 0 && (kLoaders == 1 || (xmode & 256) || (lane & 1) == L) && !(xmode & 8)) {
                     const uint32_t dst = slab_base + buf * C::kSlab + lane * (16 * C::kRB);
 #pragma unroll
                     for (int h = 0; h < C::kHalves; ++h)
@@ -885,6 +887,13 @@ __global__ void __launch_bounds__(128) tile_plan_kernel(const int *__restrict__ 
     }
 }
 
+// TODA_TS_LOADERS=1: one slab-loader warp instead of two (A/B switch)
+static int ts_env_mode() {
+    static int m = -1;
+    if (m < 0) { const char *e = getenv("TODA_TS_LOADERS"); m = (e && e[0] == '1') ? 256 : 0; }
+    return m;
+}
+
 template <int CIN, int COUT>
 int launch_ts(const __nv_bfloat16 *xb, int n_in, const int32_t *nbr, int n_out, int kvol, const TilePlan &plan, const __nv_bfloat16 *wb,
               const float *bias, const float *addend, float *y, const int32_t *out_rows, const uint32_t *tile_masks, double *bn_sums,
@@ -906,7 +915,7 @@ int launch_ts(const __nv_bfloat16 *xb, int n_in, const int32_t *nbr, int n_out, 
     }
     conv_ts_fwd_kernel<CIN, COUT><<<grid, C::kThreads, C::kSmem, st>>>(xb, nbr, n_out, kvol, plan.lidx, plan.rows, plan.cnt, plan.ngroups,
                                                                    plan.cap, map_x, map_w, bias, addend, y, out_rows, tile_masks, bn_sums,
-                                                                   num_tiles, conv_tc_debug_timeline(), conv_tc_debug_mode());
+                                                                   num_tiles, conv_tc_debug_timeline(), conv_tc_debug_mode() | ts_env_mode());
     TODA_LAUNCH_OK();
     return TODA_OK;
 }
