@@ -53,12 +53,10 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-// A lost arrival must not hang the GPU box: a wait gives up (trap) after 2^22 probes (measured ~1.5 us per probe once nothing
-// moves any more: several seconds).  The limit is
-// deliberately generous -- one of a few tens of milliseconds fired in a 2-GPU run, where the first NCCL all-reduce
-// (communicator set-up, buffer registration) overlaps the backward pass and stalls every kernel on the device far longer
-// than any wait of this kernel lasts by itself.  (A wall-clock limit read from %globaltimer cost registers in every inlined
-// wait and 10 % of the kernel's speed; the printf that names the barrier is compiled in with -DTODA_TS_VERBOSE_TIMEOUT.)
+// A lost arrival must not hang the GPU box: a wait gives up (trap) after 2^22 probes -- measured ~1.5 us per probe once
+// nothing moves any more, i.e. several seconds.  (A wall-clock limit read from %globaltimer cost registers in every inlined
+// wait and 10 % of the kernel's speed; -DTODA_TS_VERBOSE_TIMEOUT compiles in the printf that names the barrier, lists every
+// stuck waiter before trapping, and records each role's progress in shared memory.)
 #ifdef TODA_TS_VERBOSE_TIMEOUT
 __shared__ int ts_prog[32];
 #define TS_PROG(v) do { } while (0)
