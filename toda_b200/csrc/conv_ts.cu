@@ -69,6 +69,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         // (the last operand is the suspend-time hint in ns: the thread sleeps in hardware until the phase completes or the
         // time is up, so a waiting role re-issues a handful of instructions per wake-up instead of spinning next to the
         // gather warps it shares a scheduler with; an arrival wakes it at once)
+#ifdef TODA_TS_PLAIN_WAIT
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+#else
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
@@ -76,6 +85,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity), "r"(0x4000u)
             : "memory");
+#endif
         if (!done && ++spins > (1u << 22)) {
 #ifdef TODA_TS_VERBOSE_TIMEOUT
             if ((threadIdx.x & 31) == 0) {
