@@ -53,8 +53,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-// A lost arrival must not hang the GPU box: a wait gives up (trap) after 2^22 probes -- measured ~1.5 us per probe once
-// nothing moves any more, i.e. several seconds.  (A wall-clock limit read from %globaltimer cost registers in every inlined
+// A lost arrival must not hang the GPU box: a wait gives up (trap) after 2^26 probes (seconds; generous, because the first
+// NCCL all-reduce of a multi-GPU run can stall every kernel on the device for hundreds of milliseconds).  (A wall-clock limit read from %globaltimer cost registers in every inlined
 // wait and 10 % of the kernel's speed; -DTODA_TS_VERBOSE_TIMEOUT compiles in the printf that names the barrier, lists every
 // stuck waiter before trapping, and records each role's progress in shared memory.)
 #ifdef TODA_TS_VERBOSE_TIMEOUT
@@ -66,10 +66,9 @@ __shared__ int ts_prog[32];
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0, spins = 0;
     while (!done) {
-        // (the last operand is the suspend-time hint in ns: the thread sleeps in hardware until the phase completes or the
-        // time is up, so a waiting role re-issues a handful of instructions per wake-up instead of spinning next to the
-        // gather warps it shares a scheduler with; an arrival wakes it at once)
-#ifdef TODA_TS_PLAIN_WAIT
+        // (plain try_wait: the form with a suspend-time hint -- "sleep in hardware until the phase completes or the time
+        // is up" -- was used here until the end of round 2 and is implicated in the kernel's deadlocks: with it the stage-2
+        // workload hung in 10 of 12 runs, without it in 0 of 8; profiles/r02_conv_ts.md section 5)
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -77,23 +76,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-#else
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity), "r"(0x4000u)
-            : "memory");
-#endif
-        if (!done && ++spins > (1u << 22)) {
+        if (!done && ++spins > (1u << 26)) {
 #ifdef TODA_TS_VERBOSE_TIMEOUT
             if ((threadIdx.x & 31) == 0) {
                 volatile int *pg = ts_prog;
                 printf("conv_ts: mbarrier timeout smem=0x%x parity=%u block=%d warp=%d | prog mma %x L0 %x L1 %x B %x g8 %x g12 %x g16 %x g20 %x me %x\n", bar, parity, (int)blockIdx.x,
                        (int)(threadIdx.x >> 5), pg[4], pg[5], pg[7], pg[6], pg[8], pg[12], pg[16], pg[20], pg[threadIdx.x >> 5]);
             }
-            if (spins < (1u << 22) + (1u << 21)) { spins += (1u << 20); continue; }
+            if (spins < (1u << 26) + (1u << 25)) { spins += (1u << 24); continue; }
 #endif
             __trap();
         }
@@ -106,14 +96,14 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
     while (true) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(bar), "r"(parity), "r"(0x4000u)
+            : "r"(bar), "r"(parity)
             : "memory");
         if (done) break;
         __nanosleep(256);
-        if (++spins > (1u << 22)) {
+        if (++spins > (1u << 26)) {
 #ifdef TODA_TS_VERBOSE_TIMEOUT
             printf("conv_ts: mbarrier timeout (relaxed) smem=0x%x parity=%u block=%d warp=%d\n", bar, parity, (int)blockIdx.x, (int)(threadIdx.x >> 5));
 #endif

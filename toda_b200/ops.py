@@ -493,10 +493,10 @@ def rulebook_sparse(index_in: OccupancyIndex, ksize, stride, padding, tag, cin=N
 
 # Row-cache plans (toda_table_tile_plan) + the TMEM-operand kernel of conv_ts.cu: 14-36 % faster per layer than the round-1
 # cp.async / gather4 kernels (profiles/r02_conv_ts.md), bit-identical results -- and OPT-IN (TODA_TILE_PLANS=1 or
-# set_tile_plans(True)): at the end of round 2 the kernel still has a rare, input-dependent deadlock in its slab hand-off
-# that was reproduced on the second rank's frames and on the stage-2 mixed batch and not fully root-caused (DESIGN section 6,
-# profiles/r02_conv_ts.md section 5).  It gives up with a trap after a few seconds instead of hanging, but a path that can
-# abort a training step is not the default.  The default keeps the round-1 kernels, which ran every workload and 1-8 GPUs.
+# set_tile_plans(True)): the kernel deadlocked on some inputs (the second rank's frames, the stage-2 mixed batch) until the
+# last hour of round 2, when the cause was pinned on the mbarrier.try_wait form with a suspend-time hint; with the plain form
+# it has run clean since (15 bench runs), which is evidence but not a soak test (profiles/r02_conv_ts.md
+# section 5).  The default keeps the round-1 kernels, which ran every workload and 1-8 GPUs.
 import os as _os
 _TILE_PLANS = _os.environ.get("TODA_TILE_PLANS", "0") == "1"
 
