@@ -362,7 +362,10 @@ def run_ours(args, rank, world, local_rank):
         nxt = front(hp, ho, False)                   # H2D of the next batch from pinned memory, on the side stream
         return float(loss.item()), nxt               # D2H read of this step's result
     h = front(*hosts[0], False)
-    for i in range(max(2, args.warmup)):          # (the H2D path and its side-pool size classes warm up too)
+    # (the H2D path and its side-pool size classes warm up too: every pre-staged batch is copied at least once more than
+    # the pool holds, so that no first-time allocation of a staging tensor -- a cudaMalloc, i.e. a device-wide sync of
+    # ~50 ms, seen as one outlier step in 2 of ~40 runs -- can land in the timed region)
+    for i in range(max(POOL + 2, args.warmup)):
         _, h = e2e_step(h, i)
     barrier()
     e0.record()
