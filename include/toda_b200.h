@@ -76,6 +76,11 @@ int toda_index_release(void *index, int batch, int D, int H, int W, const int32_
  *   mode TODA_SELECT_SECTOR    the sector of PolarMix swap / swap_with_range (inter_domain_point_polarmix.py L76-80,
  *        L103-119): start < -arctan2(y,x) < end in float32; params_host = {start, end, dis_th, dis_mode} with
  *        dis_mode 0 = no distance test, 1 = also sqrt(x^2+y^2) < dis_th, 2 = also > dis_th
+ *   mode TODA_SELECT_BOXES     augmentor_utils.get_points_in_box (pcdet/datasets/augmentor/augmentor_utils.py L474-491)
+ *        OR-ed over M <= 96 boxes: the point is rotated by -rz about the box centre; |z - cz| <= dz/2 and
+ *        |local x|, |local y| <= half size + margin, all in float32 as numpy evaluates it; with invert != 0 this is the
+ *        point filter of intra_domain_point_mixup_cd (intra_domain_point_mixup.py L50-59).  Needs a z column (x_col + 2).
+ *        params_host = {M, margin, M x (cx, cy, cz, dx, dy, dz, rz)}
  * invert != 0 keeps the complement (np.delete / ~mask).  Kept rows keep their input order (what numpy's mask indexing
  * gives).  add_batch_col != 0 prepends the frame index as a float column (collate_batch, dataset.py L173-178), so raw
  * (N,F) frames can be shipped and collated on the device.
@@ -86,6 +91,7 @@ int toda_index_release(void *index, int batch, int D, int H, int W, const int32_
 #define TODA_SELECT_RANGE_XY 0
 #define TODA_SELECT_RECT_XY 1
 #define TODA_SELECT_SECTOR 2
+#define TODA_SELECT_BOXES 3   /* params = [M, margin, M x (cx,cy,cz,dx,dy,dz,rz)]: inside ANY box (augmentor_utils.py L474-491), M <= 96 */
 size_t toda_points_select_workspace_bytes(int n);
 int toda_points_select(const float *points, int n, int stride, int x_col, const int32_t *frame_offsets, int batch, int mode,
                        const double *params_host, int invert, int add_batch_col, float *out, int32_t *out_offsets,

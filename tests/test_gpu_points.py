@@ -108,3 +108,36 @@ def test_sector_full_frame_vs_oracle():
     for a0, a1 in [(-np.pi, -np.pi + 1.570796), (0.3, 0.3 + 1.570796), (2.2, np.pi)]:
         got, _ = ops.points_select(_t(pts), None, ops.SELECT_SECTOR, [a0, a1])
         assert np.array_equal(got.cpu().numpy(), pts[OP.sector_mask(pts, a0, a1)])
+
+
+def test_points_in_box_golden():
+    """The box test of the mixers (augmentor_utils.get_points_in_box, run by the reference itself for the golden): per box
+    the selected rows are exactly points[mask]; all boxes together = the point filter of intra_domain_point_mixup_cd."""
+    from toda_b200.pcdet_plugin.processor import points_in_boxes, remove_points_in_boxes
+    pts, boxes, masks = G["inbox/points"], G["inbox/boxes"], G["inbox/masks"]
+    tp = _t(pts)
+    for b in range(boxes.shape[0]):
+        got = points_in_boxes(tp, boxes[b:b + 1]).cpu().numpy()
+        assert np.array_equal(got, pts[masks[b]]), b
+    got = points_in_boxes(tp, boxes).cpu().numpy()
+    assert np.array_equal(got, pts[masks.any(axis=0)])
+    got = remove_points_in_boxes(tp, boxes).cpu().numpy()
+    assert np.array_equal(got, pts[~masks.any(axis=0)])
+    assert np.array_equal(got, OP.remove_points_in_boxes(pts, boxes))
+
+
+def test_points_in_boxes_full_frame_vs_oracle():
+    """A full-size frame against 150 random boxes (two chunks of the 96-box kernel limit), bit-identical to the oracle."""
+    from toda_b200 import synth
+    from toda_b200.pcdet_plugin.processor import remove_points_in_boxes
+    pts = synth.make_frame("nus_0075", 3)
+    rng = np.random.default_rng(7)
+    n_box = 150
+    centers = pts[rng.integers(0, pts.shape[0], n_box), :3] + rng.normal(0, 0.3, (n_box, 3)).astype(np.float32)
+    sizes = rng.uniform(0.5, 6.0, (n_box, 3)).astype(np.float32)
+    rz = rng.uniform(-np.pi, np.pi, (n_box, 1)).astype(np.float32)
+    boxes = np.concatenate([centers.astype(np.float32), sizes, rz], axis=1).astype(np.float32)
+    got = remove_points_in_boxes(_t(pts), boxes).cpu().numpy()
+    ref = OP.remove_points_in_boxes(pts, boxes)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+    assert 0 < ref.shape[0] < pts.shape[0]

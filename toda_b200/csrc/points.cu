@@ -4,6 +4,10 @@
 //   mode 1  rectangle      inter_domain_point_cutmix.py L45-55 (strict, thresholds in float64 as numpy promotes them)
 //   mode 2  polar sector   inter_domain_point_polarmix.py L76-80 / L103-119 (yaw = -arctan2(y, x) in float32,
 //                          strict; optional distance test against dis_th)
+//   mode 3  boxes          augmentor_utils.get_points_in_box (pcdet/datasets/augmentor/augmentor_utils.py L474-491) OR-ed over
+//                          up to 96 boxes: the point filter of intra_domain_point_mixup.py L50-59 (with `invert`) and the
+//                          box side of the mixers.  float32 arithmetic op by op as numpy does it (no FMA), cos / sin of -rz
+//                          evaluated in double on the host (math.cos / math.sin) and rounded to float32.
 // `invert` keeps the complement (np.delete / ~mask).  Optionally the batch-index column of collate_batch
 // (dataset.py L173-178) is written in the same pass (`add_batch_col`), so the host can ship raw (N,F) frames.
 // Two launches, no atomics, no inter-CTA waiting: tile = 1024 points; launch 1 writes the ballot words and per-tile
@@ -16,17 +20,31 @@ namespace {
 constexpr int kSelThreads = 256;
 constexpr int kSelTile = 1024;                 // points per CTA = 4 per thread = 32 ballot words
 
+constexpr int kSelMaxBoxes = 96;
+struct SelBox { float cx, cy, cz, hx, hy, hz, ca, sa; };   // centre, half sizes (x, y incl. margin), cos(-rz), sin(-rz)
+
 struct SelParams {
     int mode, invert;
     float lo_x, lo_y, hi_x, hi_y;              // mode 0
     double min_x, min_y, max_x, max_y;         // mode 1
     float start, end, dis_th;                  // mode 2
     int dis_mode;                              // 0 none, 1 keep dis < dis_th, 2 keep dis > dis_th
+    int nbox;                                  // mode 3
+    SelBox box[kSelMaxBoxes];
 };
 
-__device__ __forceinline__ bool sel_keep(const SelParams &p, float x, float y) {
+__device__ __forceinline__ bool sel_keep(const SelParams &p, float x, float y, float z) {
     bool k;
-    if (p.mode == 0) {
+    if (p.mode == 3) {
+        k = false;
+        for (int b = 0; b < p.nbox; ++b) {
+            const SelBox &q = p.box[b];
+            const float sx = __fsub_rn(x, q.cx), sy = __fsub_rn(y, q.cy), sz = __fsub_rn(z, q.cz);
+            const float lx = __fadd_rn(__fmul_rn(sx, q.ca), __fmul_rn(sy, -q.sa));     // shift_x * cosa + shift_y * (-sina)
+            const float ly = __fadd_rn(__fmul_rn(sx, q.sa), __fmul_rn(sy, q.ca));      // shift_x * sina + shift_y * cosa
+            k = k || (fabsf(sz) <= q.hz && fabsf(lx) <= q.hx && fabsf(ly) <= q.hy);
+        }
+    } else if (p.mode == 0) {
         k = x >= p.lo_x && x <= p.hi_x && y >= p.lo_y && y <= p.hi_y;
     } else if (p.mode == 1) {
         const double xd = (double)x, yd = (double)y;
@@ -56,7 +74,7 @@ __global__ void __launch_bounds__(kSelThreads) select_flag_kernel(const float *_
         bool k = false;
         if (i < n) {
             const float *row = points + (size_t)i * stride + x_col;
-            k = sel_keep(p, __ldg(row), __ldg(row + 1));
+            k = sel_keep(p, __ldg(row), __ldg(row + 1), p.mode == 3 ? __ldg(row + 2) : 0.f);
         }
         const uint32_t w = __ballot_sync(0xffffffffu, k);
         if (lane == 0) {
@@ -188,7 +206,8 @@ extern "C" int toda_points_select(const float *points, int n, int stride, int x_
                                   int mode, const double *params_host, int invert, int add_batch_col, float *out,
                                   int32_t *out_offsets, void *workspace, size_t workspace_bytes, void *stream) {
     TODA_CHECK_ARG(n >= 0 && stride >= 2 && stride <= 63 && x_col >= 0 && x_col + 1 < stride, "points_select: bad layout n=%d stride=%d x_col=%d", n, stride, x_col);
-    TODA_CHECK_ARG(mode >= 0 && mode <= 2 && params_host, "points_select: bad mode %d", mode);
+    TODA_CHECK_ARG(mode >= 0 && mode <= 3 && params_host, "points_select: bad mode %d", mode);
+    TODA_CHECK_ARG(mode != 3 || x_col + 2 < stride, "points_select: the box test needs a z column");
     TODA_CHECK_ARG(!frame_offsets || (batch >= 1 && batch <= 64), "points_select: batch %d outside [1, 64]", batch);
     TODA_CHECK_ARG(out_offsets && workspace && (n == 0 || (points && out)), "points_select: null pointer");
     if (workspace_bytes < toda_points_select_workspace_bytes(n)) {
@@ -203,6 +222,22 @@ extern "C" int toda_points_select(const float *points, int n, int stride, int x_
         p.lo_x = (float)params_host[0]; p.lo_y = (float)params_host[1]; p.hi_x = (float)params_host[2]; p.hi_y = (float)params_host[3];
     } else if (mode == 1) {
         p.min_x = params_host[0]; p.min_y = params_host[1]; p.max_x = params_host[2]; p.max_y = params_host[3];
+    } else if (mode == 3) {
+        // params: [number of boxes M, margin, M x (cx, cy, cz, dx, dy, dz, rz)], every value a float32 carried in a double
+        p.nbox = (int)params_host[0];
+        TODA_CHECK_ARG(p.nbox >= 0 && p.nbox <= kSelMaxBoxes, "points_select: %d boxes (at most %d per call)", p.nbox, kSelMaxBoxes);
+        const float margin = (float)params_host[1];
+        for (int b = 0; b < p.nbox; ++b) {
+            const double *g = params_host + 2 + 7 * b;
+            SelBox &q = p.box[b];
+            q.cx = (float)g[0]; q.cy = (float)g[1]; q.cz = (float)g[2];
+            q.hx = (float)g[3] / 2.0f + margin;        // dx / 2.0 + MARGIN, float32 op by op
+            q.hy = (float)g[4] / 2.0f + margin;
+            q.hz = (float)g[5] / 2.0f;                 // |z - cz| <= dz / 2.0, no margin
+            const double a = (double)(-(float)g[6]);   // math.cos(-rz) / math.sin(-rz) of the float32 heading, in double
+            q.ca = (float)cos(a);
+            q.sa = (float)sin(a);
+        }
     } else {
         p.start = (float)params_host[0]; p.end = (float)params_host[1]; p.dis_th = (float)params_host[2];
         p.dis_mode = (int)params_host[3];

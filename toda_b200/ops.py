@@ -129,7 +129,8 @@ def _workspace(tag, nbytes, device, zero=False):
 # ------------------------------------------------------------------------------------------------
 # K0 point-stream selection
 # ------------------------------------------------------------------------------------------------
-SELECT_RANGE_XY, SELECT_RECT_XY, SELECT_SECTOR = 0, 1, 2
+SELECT_RANGE_XY, SELECT_RECT_XY, SELECT_SECTOR, SELECT_BOXES = 0, 1, 2, 3
+SELECT_MAX_BOXES = 96
 
 
 def points_select(points, frame_offsets, mode, params, invert=False, add_batch_col=False, x_col=0, trim=True):

@@ -128,3 +128,31 @@ def mixup_points(points_1, points_2, lam, shuffle_idx_1, shuffle_idx_2):
         idx = torch.as_tensor(np.asarray(idx[:k]), dtype=torch.int32, device=points.device) if not torch.is_tensor(idx) else idx[:k].int()
         return ops.gather_point_rows(points, idx.contiguous())
     return torch.cat([prefix(points_1, shuffle_idx_1, lam), prefix(points_2, shuffle_idx_2, 1 - lam)], dim=0)
+
+
+def _box_params(boxes, margin):
+    b = torch.as_tensor(boxes, dtype=torch.float32).reshape(-1, boxes.shape[-1] if hasattr(boxes, "shape") else 7)[:, :7].cpu()
+    return [float(b.shape[0]), float(margin)] + [float(v) for v in b.reshape(-1).tolist()]
+
+
+def points_in_boxes(points, boxes, margin=1e-1, x_col=0):
+    """Rows of `points` that lie in ANY of `boxes` (N_box <= 96, (cx, cy, cz, dx, dy, dz, rz[, ...]) rows), input order kept:
+    the union of augmentor_utils.get_points_in_box (pcdet/datasets/augmentor/augmentor_utils.py L474-491) over the boxes.
+    The boxes (a few dozen floats) are read on the host, as the reference reads them."""
+    n_box = int(boxes.shape[0])
+    if n_box > ops.SELECT_MAX_BOXES:
+        raise ValueError("points_in_boxes: at most %d boxes per call" % ops.SELECT_MAX_BOXES)
+    out, _ = ops.points_select(points, None, ops.SELECT_BOXES, _box_params(boxes, margin), x_col=x_col)
+    return out
+
+
+def remove_points_in_boxes(points, boxes, margin=1e-1, x_col=0):
+    """The point filter of intra_domain_point_mixup_cd (intra_domain_point_mixup.py L50-59): drop every point that lies in
+    any of `boxes`.  More than 96 boxes are applied in chunks (removal composes)."""
+    n_box = int(boxes.shape[0])
+    for lo in range(0, max(n_box, 1), ops.SELECT_MAX_BOXES):
+        chunk = boxes[lo:lo + ops.SELECT_MAX_BOXES]
+        if chunk.shape[0] == 0:
+            break
+        points, _ = ops.points_select(points, None, ops.SELECT_BOXES, _box_params(chunk, margin), invert=True, x_col=x_col)
+    return points
