@@ -34,7 +34,6 @@ class InputPipeline:
         lo, hi = torch.cuda.Stream.priority_range()      # (lowest, highest): highest is the numerically smaller one
         self.stream = torch.cuda.Stream(self.device, priority=hi)
         self._started = deque()     # main-stream events, one per consume(): "the batch before this one has finished"
-        self._keep = deque(maxlen=int(__import__("os").environ.get("TODA_PIPE_KEEP", "0")) or None) if __import__("os").environ.get("TODA_PIPE_KEEP") else None
         if reserve_bytes:
             # the caching allocator keeps one pool per stream: give the side stream its blocks up front so that row
             # counts that differ from batch to batch never reach cudaMalloc (which synchronises the device)
@@ -92,6 +91,4 @@ class InputPipeline:
         main.wait_event(handle.ready)
         for t in handle.tensors:
             t.record_stream(main)      # allocated on the side stream's pool, read by main-stream kernels from now on
-        if self._keep is not None:
-            self._keep.append(handle.tensors)
         return handle.batch_dict
