@@ -5,17 +5,21 @@
 // Why another kernel: conv_tc.cu / conv_tma.cu gather every A row from L2 once per (offset, output row) -- in raster
 // order the same input row is fetched 2.5-4 times per 128-row tile (profiles/r01_feed_ab.md) -- and every A byte crosses
 // the shared-memory port twice more (written by the copy, read by the MMA).  Here
-//   * a plan-time pass (tile_plan_kernel) lists, per tile and per kz-group of offsets, the DISTINCT input rows the tile
-//     touches and rewrites the neighbour table into 16-bit slot numbers into that list;
-//   * a loader warp copies those rows ONCE (cp.async, 16-byte pieces, contiguous row runs coalesce) into a padded
-//     shared-memory slab, one offset group ahead of its use;
-//   * eight gather warps (thread = output row = TMEM lane) read their row's neighbour out of the slab (16-byte
-//     ld.shared, conflict-free thanks to the 16-byte row padding) and write it with tcgen05.st straight into TENSOR
-//     MEMORY, where tcgen05.mma takes its A operand from (the ".ts" form: A in TMEM, lane = row, two bf16 per 32-bit
-//     column).  The A tile never exists in shared memory; rows without a neighbour are zero registers.
-//   * B (weights, K-major SWIZZLE_128B) still arrives by tiled TMA; accumulators are double-buffered in TMEM and
-//     drained by four epilogue warps (bias, optional addend, BatchNorm statistics) while the next tile is multiplied.
-// TMEM map (512 columns): [0, 2*COUT) two accumulators, [256, 512) a ring of eight 32-column A blocks (64 K elements).
+//   * a plan-time pass (tile_plan_kernel) lists, per tile and per kz-group of offsets, the DISTINCT 16-row blocks of x the
+//     tile touches and rewrites the neighbour table into 16-bit slot numbers into that list;
+//   * two loader warps bring each listed block in with ONE tiled TMA box copy (hardware swizzle) into a slab, up to four
+//     offset groups ahead of their use (only the first warp talks to the slab barriers, the second follows it through a
+//     named barrier); the tile's slot table arrives by cp.async.bulk, a tile ahead;
+//   * the gather warpgroups (thread = output row = TMEM lane; 4 x 32 or 2 x 64 data registers, TsCfg) read their row's
+//     neighbour out of the slab (predicated 16-byte ld.shared: a row without a neighbour stays zero registers) and write
+//     it with tcgen05.st straight into TENSOR MEMORY, where tcgen05.mma takes its A operand from (the ".ts" form: A in
+//     TMEM, lane = row, two bf16 per 32-bit column).  The A tile never exists in shared memory;
+//   * B (weights, K-major SWIZZLE_128B) arrives by tiled TMA (resident for the life of the CTA when all K blocks fit in
+//     56 KB); accumulators are double-buffered in TMEM and drained by four epilogue warps (bias, optional addend,
+//     BatchNorm statistics) while the next tile is multiplied.
+// TMEM map (512 columns): [0, 2*COUT) two accumulators, then a ring of 4-6 A slots of 2 x 32 columns (ARing).
+// OPT-IN (TODA_TILE_PLANS=1): see ops.py and profiles/r02_conv_ts.md section 5 for the deadlock history of this kernel and
+// why every wait uses the plain mbarrier.try_wait.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
