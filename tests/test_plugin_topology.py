@@ -83,3 +83,16 @@ def test_point_preprocessor_two_phase_protocol_on_cpu():
     assert pp.data_processor_queue[1](data_dict={"points": marker})["points"] is marker
     with pytest.raises(NotImplementedError):
         PointPreprocessor([Cfg(NAME="transform_points_to_voxels", VOXEL_SIZE=[0.1, 0.1, 0.2])], np.zeros(6, np.float32), True, 5)
+
+
+def test_box_params_packing_is_host_logic():
+    """K0 box mode parameters: count, margin, then seven float32 values per box; extra gt_boxes columns are dropped."""
+    import numpy as np
+    import torch
+    from toda_b200.pcdet_plugin.processor import _box_params
+    b = np.arange(16, dtype=np.float32).reshape(2, 8)
+    want = [2.0, float(np.float32(0.1))] + [0, 1, 2, 3, 4, 5, 6, 8, 9, 10, 11, 12, 13, 14]
+    got = _box_params(b, np.float32(0.1))
+    assert got == [float(v) for v in want]
+    assert _box_params(torch.from_numpy(b), np.float32(0.1)) == got
+    assert _box_params(b[:0], 0.1) == [0.0, 0.1]

@@ -131,7 +131,10 @@ def mixup_points(points_1, points_2, lam, shuffle_idx_1, shuffle_idx_2):
 
 
 def _box_params(boxes, margin):
-    b = torch.as_tensor(boxes, dtype=torch.float32).reshape(-1, boxes.shape[-1] if hasattr(boxes, "shape") else 7)[:, :7].cpu()
+    """params of TODA_SELECT_BOXES: [M, margin, M x (cx, cy, cz, dx, dy, dz, rz)] from (M, >= 7) boxes (extra columns, e.g. the
+    class index of gt_boxes, are dropped); values are float32, as the reference's gt_boxes are."""
+    b = torch.as_tensor(boxes, dtype=torch.float32).cpu()
+    b = b.reshape(-1, b.shape[-1])[:, :7]
     return [float(b.shape[0]), float(margin)] + [float(v) for v in b.reshape(-1).tolist()]
 
 
